@@ -1,0 +1,378 @@
+// C ABI of libconfild_cnf.so (see include/confild_cnf.h): argument checks, kernel selection, launches.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/confild_cnf.h"
+#include "layout.cuh"
+#include "pack.cuh"
+#include "simt.cuh"
+#include "tc_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CNF_CUDA(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail(CNF_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+int check_dims(const cnf_dims* d) {
+  if (!d) return fail(CNF_ERR_INVALID_ARGUMENT, "dims is NULL");
+  if (d->cin < 1 || d->L < 1 || d->H < 1 || d->nl < 0 || d->cout < 1)
+    return fail(CNF_ERR_INVALID_ARGUMENT, "non-positive dimension (cin=%d L=%d H=%d nl=%d cout=%d)", d->cin, d->L,
+                d->H, d->nl, d->cout);
+  return CNF_OK;
+}
+
+bool tc_ok(const cnf_dims& d) {
+  return cnf::tc_shape_ok(d.H) && d.nl >= 1 && d.cin <= 4 && d.cout <= 4;
+}
+
+struct DeviceInfo {
+  int sms = 0;
+  int max_smem_optin = 0;
+};
+int device_info(DeviceInfo* info) {
+  int dev = 0;
+  CNF_CUDA(cudaGetDevice(&dev));
+  CNF_CUDA(cudaDeviceGetAttribute(&info->sms, cudaDevAttrMultiProcessorCount, dev));
+  CNF_CUDA(cudaDeviceGetAttribute(&info->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  return CNF_OK;
+}
+
+size_t simt_smem_bytes(const cnf_dims& d) {
+  const int extra = d.cin > d.cout ? d.cin : d.cout;
+  return ((size_t)2 * cnf::kSimtTM * (d.H + 1) + (size_t)cnf::kSimtTM * extra) * sizeof(float);
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// Launch plan for a tensor-core kernel: ring depth, shared memory, CTAs per SM, grid.
+struct TcPlan {
+  int stages = 0;
+  size_t smem = 0;
+  int ctas_per_sm = 1;
+  int64_t grid = 0;
+  unsigned tmem_cols = 0;
+};
+
+template <int H, int PREC>
+int make_tc_plan(const DeviceInfo& di, int64_t tiles, TcPlan* plan) {
+  using C = cnf::TcCfg<H, PREC>;
+  // Two resident CTAs per SM (one runs its MMAs while the other runs its sine epilogue) whenever the
+  // A operand leaves room for a >= 2-deep weight ring in half the shared memory; otherwise one CTA.
+  const size_t per_sm = (size_t)di.max_smem_optin + 1024;  // opt-in limit is per block; SM has 1 KiB more per block
+  int want = env_int("CNF_TC_CTAS_PER_SM", 0);
+  int best_ctas = 1, best_stages = 0;
+  for (int ctas = (want > 0 ? want : 2); ctas >= 1; --ctas) {
+    const size_t budget = per_sm / ctas - 1024;
+    const size_t fixed = cnf::tc_smem_bytes<H, PREC>(0);
+    if (budget <= fixed) continue;
+    int stages = (int)((budget - fixed) / cnf::kStageBytes);
+    if (stages > cnf::kTcMaxStages) stages = cnf::kTcMaxStages;
+    if ((int)C::kTmemCols * ctas > 512) continue;
+    if (stages >= 2) { best_ctas = ctas; best_stages = stages; break; }
+  }
+  if (best_stages < 2) return fail(CNF_ERR_UNSUPPORTED, "H=%d precision=%d does not fit in shared memory", H, PREC);
+  const int forced = env_int("CNF_TC_STAGES", 0);
+  if (forced >= 2 && forced <= best_stages) best_stages = forced;
+  plan->stages = best_stages;
+  plan->ctas_per_sm = best_ctas;
+  plan->smem = cnf::tc_smem_bytes<H, PREC>(best_stages);
+  plan->tmem_cols = C::kTmemCols;
+  const int64_t cap = (int64_t)di.sms * best_ctas;
+  plan->grid = tiles < cap ? tiles : cap;
+  return CNF_OK;
+}
+
+template <int H, int PREC, bool STASH, bool REDUCE>
+int launch_tc_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs, const float* shift,
+                      float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
+  TcPlan plan;
+  if (int rc = make_tc_plan<H, PREC>(di, tiles, &plan)) return rc;
+  auto kern = cnf::tc_forward_kernel<H, PREC, STASH, REDUCE>;
+  CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  kern<<<(unsigned)plan.grid, cnf::kTcThreads, plan.smem, st>>>(d, packed, coords, cfs, shift, out,
+                                                                reinterpret_cast<__half*>(stash), T, P, plan.stages);
+  CNF_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+template <int H, int PREC>
+int dispatch_tc_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs,
+                        const float* shift, float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
+  const bool reduce = env_int("CNF_TC_REDUCE", 1) != 0;
+  if (stash) {
+    return reduce ? launch_tc_forward<H, PREC, true, true>(d, packed, coords, cfs, shift, out, stash, T, P, st)
+                  : launch_tc_forward<H, PREC, true, false>(d, packed, coords, cfs, shift, out, stash, T, P, st);
+  }
+  return reduce ? launch_tc_forward<H, PREC, false, true>(d, packed, coords, cfs, shift, out, stash, T, P, st)
+                : launch_tc_forward<H, PREC, false, false>(d, packed, coords, cfs, shift, out, stash, T, P, st);
+}
+
+template <int PREC>
+int dispatch_tc_forward_h(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs,
+                          const float* shift, float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
+  switch (d.H) {
+    case 128: return dispatch_tc_forward<128, PREC>(d, packed, coords, cfs, shift, out, stash, T, P, st);
+    case 256: return dispatch_tc_forward<256, PREC>(d, packed, coords, cfs, shift, out, stash, T, P, st);
+    case 384: return dispatch_tc_forward<384, PREC>(d, packed, coords, cfs, shift, out, stash, T, P, st);
+  }
+  return fail(CNF_ERR_UNSUPPORTED, "no tensor-core kernel for H=%d", d.H);
+}
+
+template <int H>
+int launch_tc_backward(const cnf_dims& d, const uint8_t* packed, const float* gout, const void* stash, float* gshift,
+                       int64_t T, int64_t P, cudaStream_t st) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
+  TcPlan plan;
+  if (int rc = make_tc_plan<H, CNF_PREC_BF16X3>(di, tiles, &plan)) return rc;
+  auto kern = cnf::tc_backward_kernel<H>;
+  CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  kern<<<(unsigned)plan.grid, cnf::kTcThreads, plan.smem, st>>>(d, packed, gout, reinterpret_cast<const __half*>(stash),
+                                                                gshift, T, P, plan.stages);
+  CNF_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+int64_t simt_grid(int64_t tiles, int sms) {
+  const int64_t cap = (int64_t)sms * 4;
+  return tiles < cap ? tiles : cap;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cnf_abi_version(void) { return CNF_ABI_VERSION; }
+
+const char* cnf_last_error(void) { return g_err; }
+
+int cnf_tc_supported(const cnf_dims* dims) {
+  if (check_dims(dims)) return 0;
+  return tc_ok(*dims) ? 1 : 0;
+}
+
+int cnf_param_count(const cnf_dims* dims, size_t* count) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!count) return fail(CNF_ERR_INVALID_ARGUMENT, "count is NULL");
+  *count = cnf::make_param_offsets(*dims).total;
+  return CNF_OK;
+}
+
+int cnf_packed_bytes(const cnf_dims* dims, size_t* bytes) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!bytes) return fail(CNF_ERR_INVALID_ARGUMENT, "bytes is NULL");
+  *bytes = cnf::make_layout(*dims).total;
+  return CNF_OK;
+}
+
+int cnf_pack_weights(const cnf_dims* dims, const float* d_params_flat, float w0, void* d_packed, size_t packed_bytes,
+                     void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!d_params_flat || !d_packed) return fail(CNF_ERR_INVALID_ARGUMENT, "NULL device pointer");
+  const cnf::PackedLayout lay = cnf::make_layout(*dims);
+  if (packed_bytes < lay.total)
+    return fail(CNF_ERR_BUFFER_TOO_SMALL, "packed buffer has %zu bytes, need %zu", packed_bytes, lay.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* packed = static_cast<uint8_t*>(d_packed);
+  cnf::pack_fp32_kernel<<<296, 256, 0, st>>>(*dims, d_params_flat, w0, packed);
+  CNF_CUDA(cudaGetLastError());
+  if (cnf::tc_shape_ok(dims->H) && dims->nl >= 1) {
+    for (int mode = 0; mode < 3; ++mode) {
+      cnf::pack_tc_kernel<<<592, 256, 0, st>>>(*dims, d_params_flat, w0, packed, mode);
+      CNF_CUDA(cudaGetLastError());
+    }
+  }
+  return CNF_OK;
+}
+
+int cnf_film_shift(const cnf_dims* dims, const void* d_packed, const float* d_latents, int64_t T, float* d_shift,
+                   void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!d_packed || !d_latents || !d_shift) return fail(CNF_ERR_INVALID_ARGUMENT, "NULL device pointer");
+  if (T < 1) return fail(CNF_ERR_INVALID_ARGUMENT, "T=%lld", (long long)T);
+  const cnf::PackedLayout lay = cnf::make_layout(*dims);
+  const uint8_t* packed = static_cast<const uint8_t*>(d_packed);
+  const int N = (dims->nl + 1) * dims->H;
+  dim3 grid((N + 63) / 64, (unsigned)((T + 63) / 64));
+  cnf::simt_gemm_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_latents, reinterpret_cast<const float*>(packed + lay.v_cat),
+      reinterpret_cast<const float*>(packed + lay.b_shift), d_shift, T, N, dims->L);
+  CNF_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+int cnf_film_shift_backward(const cnf_dims* dims, const void* d_packed, const float* d_gshift, int64_t T,
+                            float* d_glatents, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!d_packed || !d_gshift || !d_glatents) return fail(CNF_ERR_INVALID_ARGUMENT, "NULL device pointer");
+  if (T < 1) return fail(CNF_ERR_INVALID_ARGUMENT, "T=%lld", (long long)T);
+  const cnf::PackedLayout lay = cnf::make_layout(*dims);
+  const uint8_t* packed = static_cast<const uint8_t*>(d_packed);
+  const int K = (dims->nl + 1) * dims->H;
+  dim3 grid((dims->L + 63) / 64, (unsigned)((T + 63) / 64));
+  cnf::simt_gemm_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_gshift, reinterpret_cast<const float*>(packed + lay.v_cat), nullptr, d_glatents, T, dims->L, K);
+  CNF_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+int cnf_stash_bytes(const cnf_dims* dims, int precision, int64_t T, int64_t P, size_t* bytes) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!bytes) return fail(CNF_ERR_INVALID_ARGUMENT, "bytes is NULL");
+  if (T < 1 || P < 1) return fail(CNF_ERR_INVALID_ARGUMENT, "T=%lld P=%lld", (long long)T, (long long)P);
+  size_t esize;
+  switch (precision) {
+    case CNF_PREC_FP32: esize = 4; break;
+    case CNF_PREC_BF16X3:
+    case CNF_PREC_FP16: esize = 2; break;
+    default: return fail(CNF_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+  }
+  *bytes = (size_t)T * (size_t)P * (size_t)(dims->nl + 1) * (size_t)dims->H * esize;
+  return CNF_OK;
+}
+
+int cnf_forward(const cnf_dims* dims, const void* d_packed, int precision, const float* d_coords,
+                int64_t coord_frame_stride, const float* d_shift, float* d_out, int64_t T, int64_t P, void* d_stash,
+                size_t stash_bytes, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!d_packed || !d_coords || !d_shift || !d_out) return fail(CNF_ERR_INVALID_ARGUMENT, "NULL device pointer");
+  if (T < 1 || P < 1) return fail(CNF_ERR_INVALID_ARGUMENT, "T=%lld P=%lld", (long long)T, (long long)P);
+  if (coord_frame_stride < 0) return fail(CNF_ERR_INVALID_ARGUMENT, "negative coord_frame_stride");
+  if (d_stash) {
+    size_t need = 0;
+    if (int rc = cnf_stash_bytes(dims, precision, T, P, &need)) return rc;
+    if (stash_bytes < need) return fail(CNF_ERR_BUFFER_TOO_SMALL, "stash has %zu bytes, need %zu", stash_bytes, need);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* packed = static_cast<const uint8_t*>(d_packed);
+  if (precision == CNF_PREC_FP32) {
+    DeviceInfo di;
+    if (int rc = device_info(&di)) return rc;
+    const size_t smem = simt_smem_bytes(*dims);
+    if (smem > (size_t)di.max_smem_optin)
+      return fail(CNF_ERR_UNSUPPORTED, "H=%d needs %zu bytes of shared memory (> %d)", dims->H, smem, di.max_smem_optin);
+    const int64_t tiles = T * ((P + cnf::kSimtTM - 1) / cnf::kSimtTM);
+    const unsigned grid = (unsigned)simt_grid(tiles, di.sms);
+    if (d_stash) {
+      CNF_CUDA(cudaFuncSetAttribute(cnf::simt_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cnf::simt_forward_kernel<true><<<grid, 256, smem, st>>>(*dims, packed, d_coords, coord_frame_stride, d_shift,
+                                                             d_out, static_cast<float*>(d_stash), T, P);
+    } else {
+      CNF_CUDA(cudaFuncSetAttribute(cnf::simt_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cnf::simt_forward_kernel<false><<<grid, 256, smem, st>>>(*dims, packed, d_coords, coord_frame_stride, d_shift,
+                                                              d_out, nullptr, T, P);
+    }
+    CNF_CUDA(cudaGetLastError());
+    return CNF_OK;
+  }
+  if (precision != CNF_PREC_BF16X3 && precision != CNF_PREC_FP16)
+    return fail(CNF_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+  if (!tc_ok(*dims))
+    return fail(CNF_ERR_UNSUPPORTED,
+                "tensor-core path needs H in {128,256,384}, nl>=1, cin<=4, cout<=4 (got H=%d nl=%d cin=%d cout=%d); "
+                "use CNF_PREC_FP32",
+                dims->H, dims->nl, dims->cin, dims->cout);
+  if (precision == CNF_PREC_BF16X3)
+    return dispatch_tc_forward_h<CNF_PREC_BF16X3>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out, d_stash,
+                                                  T, P, st);
+  return dispatch_tc_forward_h<CNF_PREC_FP16>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out, d_stash, T,
+                                              P, st);
+}
+
+int cnf_backward(const cnf_dims* dims, const void* d_packed, int precision, const float* d_gout, const void* d_stash,
+                 size_t stash_bytes, float* d_gshift, int64_t T, int64_t P, void* stream) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!d_packed || !d_gout || !d_stash || !d_gshift) return fail(CNF_ERR_INVALID_ARGUMENT, "NULL device pointer");
+  if (T < 1 || P < 1) return fail(CNF_ERR_INVALID_ARGUMENT, "T=%lld P=%lld", (long long)T, (long long)P);
+  size_t need = 0;
+  if (int rc = cnf_stash_bytes(dims, precision, T, P, &need)) return rc;
+  if (stash_bytes < need) return fail(CNF_ERR_BUFFER_TOO_SMALL, "stash has %zu bytes, need %zu", stash_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* packed = static_cast<const uint8_t*>(d_packed);
+  const size_t gbytes = (size_t)T * (size_t)(dims->nl + 1) * (size_t)dims->H * sizeof(float);
+  CNF_CUDA(cudaMemsetAsync(d_gshift, 0, gbytes, st));
+  if (precision == CNF_PREC_FP32) {
+    DeviceInfo di;
+    if (int rc = device_info(&di)) return rc;
+    const size_t smem = simt_smem_bytes(*dims);
+    if (smem > (size_t)di.max_smem_optin)
+      return fail(CNF_ERR_UNSUPPORTED, "H=%d needs %zu bytes of shared memory (> %d)", dims->H, smem, di.max_smem_optin);
+    const int64_t tiles = T * ((P + cnf::kSimtTM - 1) / cnf::kSimtTM);
+    CNF_CUDA(cudaFuncSetAttribute(cnf::simt_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cnf::simt_backward_kernel<<<(unsigned)simt_grid(tiles, di.sms), 256, smem, st>>>(
+        *dims, packed, d_gout, static_cast<const float*>(d_stash), d_gshift, T, P);
+    CNF_CUDA(cudaGetLastError());
+    return CNF_OK;
+  }
+  if (!tc_ok(*dims))
+    return fail(CNF_ERR_UNSUPPORTED, "tensor-core path unsupported for H=%d nl=%d cin=%d cout=%d; use CNF_PREC_FP32",
+                dims->H, dims->nl, dims->cin, dims->cout);
+  switch (dims->H) {
+    case 128: return launch_tc_backward<128>(*dims, packed, d_gout, d_stash, d_gshift, T, P, st);
+    case 256: return launch_tc_backward<256>(*dims, packed, d_gout, d_stash, d_gshift, T, P, st);
+    case 384: return launch_tc_backward<384>(*dims, packed, d_gout, d_stash, d_gshift, T, P, st);
+  }
+  return fail(CNF_ERR_UNSUPPORTED, "no tensor-core kernel for H=%d", dims->H);
+}
+
+int cnf_query_launch(const cnf_dims* dims, int precision, int64_t T, int64_t P, int64_t* values, int n) {
+  if (int rc = check_dims(dims)) return rc;
+  if (!values || n < 1) return fail(CNF_ERR_INVALID_ARGUMENT, "values is NULL or n < 1");
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  int64_t v[7] = {di.sms, 0, 0, 0, 0, 0, 0};
+  if (precision == CNF_PREC_FP32) {
+    const int64_t tiles = T * ((P + cnf::kSimtTM - 1) / cnf::kSimtTM);
+    v[1] = simt_grid(tiles, di.sms);
+    v[2] = 256;
+    v[3] = (int64_t)simt_smem_bytes(*dims);
+    v[4] = 0;
+    v[5] = 0;
+    v[6] = cnf::kSimtTM;
+  } else {
+    if (!tc_ok(*dims)) return fail(CNF_ERR_UNSUPPORTED, "tensor-core path unsupported for these dims");
+    const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
+    TcPlan plan;
+    int rc = CNF_ERR_UNSUPPORTED;
+    const bool x3 = precision == CNF_PREC_BF16X3;
+    switch (dims->H) {
+      case 128: rc = x3 ? make_tc_plan<128, CNF_PREC_BF16X3>(di, tiles, &plan) : make_tc_plan<128, CNF_PREC_FP16>(di, tiles, &plan); break;
+      case 256: rc = x3 ? make_tc_plan<256, CNF_PREC_BF16X3>(di, tiles, &plan) : make_tc_plan<256, CNF_PREC_FP16>(di, tiles, &plan); break;
+      case 384: rc = x3 ? make_tc_plan<384, CNF_PREC_BF16X3>(di, tiles, &plan) : make_tc_plan<384, CNF_PREC_FP16>(di, tiles, &plan); break;
+    }
+    if (rc) return rc;
+    v[1] = plan.grid;
+    v[2] = cnf::kTcThreads;
+    v[3] = (int64_t)plan.smem;
+    v[4] = plan.ctas_per_sm;
+    v[5] = plan.tmem_cols;
+    v[6] = cnf::kTileM;
+  }
+  for (int i = 0; i < n && i < 7; ++i) values[i] = v[i];
+  return CNF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+// CUDA-core fp32 kernels: the FiLM-shift GEMMs (always used) and the CNF_PREC_FP32 decode /
+// backward chain (exact-order GPU reference, any hidden width).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "layout.cuh"
+
+namespace cnf {
+
+// ------------------------------------------------------------------------------------------
+// C[m][n] = sum_k A[m][k] * Bop[k][n] (+ bias[n]);  B_NK: B stored [N][K] (row-dot), else [K][N].
+// 64x64 output tile per 256-thread block, 4x4 outputs per thread, K staged 16 at a time.
+template <bool B_NK>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                        const float* __restrict__ bias, float* __restrict__ C,
+                                                        int64_t M, int N, int K) {
+  __shared__ float As[16][65];
+  __shared__ float Bs[16][65];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int64_t m0 = (int64_t)blockIdx.y * 64;
+  const int n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      {
+        const int m = e / 16, k = e % 16;
+        As[k][m] = (m0 + m < M && k0 + k < K) ? A[(m0 + m) * K + k0 + k] : 0.f;
+      }
+      if (B_NK) {
+        const int n = e / 16, k = e % 16;
+        Bs[k][n] = (n0 + n < N && k0 + k < K) ? B[(size_t)(n0 + n) * K + k0 + k] : 0.f;
+      } else {
+        const int k = e / 64, n = e % 64;
+        Bs[k][n] = (n0 + n < N && k0 + k < K) ? B[(size_t)(k0 + k) * N + n0 + n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) C[m * N + n] = acc[i][j] + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int kSimtTM = 64;  // points per block
+
+// out = A(TMxH, smem) * W(HxH, global, [k][n] layout), one 128-column block at a time.
+// Thread (ty,tx): rows ty*4..+3, columns cb*128 + tx + 16*j.
+template <typename Epi>
+__device__ __forceinline__ void simt_layer(const float* __restrict__ hin, int ld, const float* __restrict__ Wkn, int H,
+                                           Epi epi) {
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  for (int cb = 0; cb < H; cb += 128) {
+    float acc[4][8] = {};
+    for (int k = 0; k < H; ++k) {
+      float a[4], w[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = hin[(ty * 4 + i) * ld + k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = cb + tx + 16 * j;
+        w[j] = (n < H) ? __ldg(Wkn + (size_t)k * H + n) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = cb + tx + 16 * j;
+        if (n < H) epi(ty * 4 + i, n, acc[i][j]);
+      }
+  }
+}
+
+// Forward chain in fp32.  Dynamic smem: 2 * TM * (H+1) floats + TM * cin floats.
+template <bool STASH>
+__global__ void __launch_bounds__(256) simt_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
+                                                           const float* __restrict__ coords,
+                                                           int64_t coord_frame_stride, const float* __restrict__ shift,
+                                                           float* __restrict__ out, float* __restrict__ stash,
+                                                           int64_t T, int64_t P) {
+  extern __shared__ float smem_f[];
+  const PackedLayout lay = make_layout(d);
+  const int H = d.H, nl = d.nl, cin = d.cin, cout = d.cout, ld = H + 1;
+  float* hA = smem_f;
+  float* hB = hA + kSimtTM * ld;
+  float* xs = hB + kSimtTM * ld;
+  const float* w_first = reinterpret_cast<const float*>(packed + lay.w_first);
+  const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
+  const float* b_out = reinterpret_cast<const float*>(packed + lay.b_out);
+  const float* w_hid_t = reinterpret_cast<const float*>(packed + lay.w_hid_t);
+  const int64_t PB = (P + kSimtTM - 1) / kSimtTM;
+  const int64_t tiles = T * PB;
+  const int tid = threadIdx.x;
+  const int64_t SH = (int64_t)(nl + 1) * H;
+
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t t = tile / PB, p0 = (tile % PB) * kSimtTM;
+    const float* cbase = coords + t * coord_frame_stride;
+    const float* sh = shift + t * SH;
+    __syncthreads();  // previous tile's readers of xs / h buffers are done
+    for (int e = tid; e < kSimtTM * cin; e += 256) {
+      const int64_t p = p0 + e / cin;
+      xs[e] = (p < P) ? cbase[p * cin + e % cin] : 0.f;
+    }
+    __syncthreads();
+    // layer 0 (K = cin)
+    for (int e = tid; e < kSimtTM * H; e += 256) {
+      const int r = e / H, n = e % H;
+      float z = sh[n];
+      for (int j = 0; j < cin; ++j) z = fmaf(w_first[n * cin + j], xs[r * cin + j], z);
+      float s, c;
+      sincosf(z, &s, &c);
+      hA[r * ld + n] = s;
+      if (STASH && p0 + r < P) stash[((t * P + p0 + r) * (nl + 1) + 0) * H + n] = c;
+    }
+    __syncthreads();
+    float* hin = hA;
+    float* hout = hB;
+    for (int l = 1; l <= nl; ++l) {
+      const float* Wkn = w_hid_t + (size_t)(l - 1) * H * H;
+      const float* shl = sh + (size_t)l * H;
+      simt_layer(hin, ld, Wkn, H, [&](int r, int n, float acc) {
+        float s, c;
+        sincosf(acc + shl[n], &s, &c);
+        hout[r * ld + n] = s;
+        if (STASH && p0 + r < P) stash[((t * P + p0 + r) * (nl + 1) + l) * H + n] = c;
+      });
+      __syncthreads();
+      float* tmp = hin;
+      hin = hout;
+      hout = tmp;
+    }
+    // linear head
+    for (int e = tid; e < kSimtTM * cout; e += 256) {
+      const int r = e / cout, o = e % cout;
+      if (p0 + r >= P) continue;
+      float y = b_out[o];
+      for (int n = 0; n < H; ++n) y = fmaf(w_out[o * H + n], hin[r * ld + n], y);
+      out[(t * P + p0 + r) * cout + o] = y;
+    }
+  }
+}
+
+// Backward to the FiLM shifts in fp32.  gshift must be zero on entry.
+// Dynamic smem: 2 * TM * (H+1) floats + TM * cout floats.
+__global__ void __launch_bounds__(256) simt_backward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
+                                                            const float* __restrict__ gout,
+                                                            const float* __restrict__ stash,
+                                                            float* __restrict__ gshift, int64_t T, int64_t P) {
+  extern __shared__ float smem_f[];
+  const PackedLayout lay = make_layout(d);
+  const int H = d.H, nl = d.nl, cout = d.cout, ld = H + 1;
+  float* dA = smem_f;
+  float* dB = dA + kSimtTM * ld;
+  float* gy = dB + kSimtTM * ld;
+  const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
+  const float* w_hid = reinterpret_cast<const float*>(packed + lay.w_hid);
+  const int64_t PB = (P + kSimtTM - 1) / kSimtTM;
+  const int64_t tiles = T * PB;
+  const int tid = threadIdx.x;
+  const int64_t SH = (int64_t)(nl + 1) * H;
+
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t t = tile / PB, p0 = (tile % PB) * kSimtTM;
+    float* gs = gshift + t * SH;
+    __syncthreads();
+    for (int e = tid; e < kSimtTM * cout; e += 256) {
+      const int64_t p = p0 + e / cout;
+      gy[e] = (p < P) ? gout[(t * P + p) * cout + e % cout] : 0.f;
+    }
+    __syncthreads();
+    // delta_nl = (gy * Wout) .* cos_nl ; column sums -> gshift[nl]
+    for (int n = tid; n < H; n += 256) {
+      float colsum = 0.f;
+      for (int r = 0; r < kSimtTM; ++r) {
+        float g = 0.f;
+        for (int o = 0; o < cout; ++o) g = fmaf(gy[r * cout + o], w_out[o * H + n], g);
+        const float c = (p0 + r < P) ? stash[((t * P + p0 + r) * (nl + 1) + nl) * H + n] : 0.f;
+        const float dl = g * c;
+        dA[r * ld + n] = dl;
+        colsum += dl;
+      }
+      atomicAdd(gs + (size_t)nl * H + n, colsum);
+    }
+    __syncthreads();
+    float* din = dA;
+    float* dout = dB;
+    for (int l = nl; l >= 1; --l) {
+      // g[r][k_in] = sum_{n_out} delta_l[r][n_out] * W_l[n_out][k_in]; delta_{l-1} = g .* cos_{l-1}
+      const float* Wnk = w_hid + (size_t)(l - 1) * H * H;
+      simt_layer(din, ld, Wnk, H, [&](int r, int n, float acc) {
+        const float c = (p0 + r < P) ? stash[((t * P + p0 + r) * (nl + 1) + (l - 1)) * H + n] : 0.f;
+        dout[r * ld + n] = acc * c;
+      });
+      __syncthreads();
+      for (int n = tid; n < H; n += 256) {
+        float colsum = 0.f;
+        for (int r = 0; r < kSimtTM; ++r) colsum += dout[r * ld + n];
+        atomicAdd(gs + (size_t)(l - 1) * H + n, colsum);
+      }
+      __syncthreads();
+      float* tmp = din;
+      din = dout;
+      dout = tmp;
+    }
+  }
+}
+
+}  // namespace cnf

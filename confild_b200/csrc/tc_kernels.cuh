@@ -1,0 +1,498 @@
+// tcgen05 / TMEM kernels for the hidden-layer chain of the FiLM-SIREN decoder (sm_100a).
+//
+// One CTA decodes 128-point tiles of one frame at a time:
+//   warps 0-3  (128 threads) "epilogue": thread r owns query point r of the tile (TMEM lane r).
+//              Layer 0 (K = cin) on CUDA cores; for each hidden layer: tcgen05.ld the fp32
+//              accumulator, add the FiLM shift, range-reduce, MUFU sin, split into bf16 hi/lo (or
+//              fp16) and write the next layer's A operand into shared memory in the K-major
+//              SWIZZLE_128B layout; last layer: dot with the output head in registers.
+//   warp 4     one elected thread issues tcgen05.mma (M=128, N=128, K=16) for every
+//              (row block, K slab, hi/lo pass) of the layer, accumulators in TMEM.
+//   warp 5     one elected thread streams the pre-swizzled 16 KiB weight stages from L2 into a
+//              shared-memory ring with 1-D bulk TMA copies (cp.async.bulk + mbarrier tx bytes).
+// Hand-shakes: b_full/b_empty per ring slot, a_full (A operand written, 128 arrivals),
+// d_full (layer's MMAs complete, tcgen05.commit).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "layout.cuh"
+#include "ptx.cuh"
+
+namespace cnf {
+
+constexpr int kTcThreads = 192;
+constexpr int kTcMaxStages = 12;
+
+template <int H, int PREC>
+struct TcCfg {
+  static constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
+  static constexpr int kParts = kSplit ? 2 : 1;
+  static constexpr int kSlabs = H / kSlabK;
+  static constexpr int kNBlocks = H / kStageRows;
+  static constexpr int kAPartBytes = kSlabs * kTileM * 128;  // one 128 x H 16-bit operand
+  static constexpr int kABytes = kParts * kAPartBytes;
+  static constexpr int kStagesPerLayer = kNBlocks * kSlabs * kParts;
+  static constexpr uint32_t kTmemCols = H <= 128 ? 128u : (H <= 256 ? 256u : 512u);
+  static constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, kStageRows);
+};
+
+struct TcSmemTail {  // lives after the A operand and the weight ring
+  uint64_t b_full[kTcMaxStages];
+  uint64_t b_empty[kTcMaxStages];
+  uint64_t a_full;
+  uint64_t d_full;
+  uint32_t tmem_base;
+};
+
+template <int H, int PREC>
+__host__ __device__ constexpr size_t tc_smem_bytes(int num_stages) {
+  return 1024 /*alignment slack*/ + (size_t)TcCfg<H, PREC>::kABytes + (size_t)num_stages * kStageBytes +
+         sizeof(TcSmemTail);
+}
+
+// ------------------------------------------------------------------ shared pieces
+// Issue all MMAs of one hidden layer (single thread).  `slot`/`phase` walk the weight ring.
+template <int H, int PREC>
+__device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_addr, uint32_t tmem_d, TcSmemTail* tail,
+                                               int num_stages, int& slot, uint32_t& phase) {
+  using C = TcCfg<H, PREC>;
+#pragma unroll 1
+  for (int nb = 0; nb < C::kNBlocks; ++nb) {
+#pragma unroll 1
+    for (int ks = 0; ks < C::kSlabs; ++ks) {
+      const uint64_t a_hi = ptx::make_desc_k_sw128(a_addr + ks * (kTileM * 128));
+      const uint64_t a_lo = ptx::make_desc_k_sw128(a_addr + C::kAPartBytes + ks * (kTileM * 128));
+      // weights, high part (or the only part): pairs with a_hi and a_lo
+      ptx::mbar_wait(&tail->b_full[slot], phase);
+      ptx::tc_fence_after();
+      {
+        const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {  // 4 x K=16 inside the 128-byte row: +32 bytes = +2 in the address field
+          ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, (ks | kk) != 0);
+          if (C::kSplit) ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_lo + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
+        }
+      }
+      ptx::umma_commit(&tail->b_empty[slot]);
+      if (++slot == num_stages) { slot = 0; phase ^= 1u; }
+      if (C::kSplit) {  // weights, low part: pairs with a_hi only
+        ptx::mbar_wait(&tail->b_full[slot], phase);
+        ptx::tc_fence_after();
+        const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
+        ptx::umma_commit(&tail->b_empty[slot]);
+        if (++slot == num_stages) { slot = 0; phase ^= 1u; }
+      }
+    }
+  }
+  ptx::umma_commit(&tail->d_full);
+}
+
+// Convert 32 activations (columns c0..c0+31 of this thread's row) to the 16-bit operand format and
+// store them into the A operand (K-major SWIZZLE_128B): 4 chunks of 16 bytes per part.
+template <int H, int PREC>
+__device__ __forceinline__ void tc_store_a(uint8_t* a_smem, int row, int c0, const float (&h)[32]) {
+  using C = TcCfg<H, PREC>;
+  uint8_t* rowp = a_smem + (c0 / kSlabK) * (kTileM * 128) + row * 128;
+  const uint32_t cbase = (c0 % kSlabK) / 8;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = h[q * 8 + 2 * e], x1 = h[q * 8 + 2 * e + 1];
+      if (C::kSplit) {
+        hi[e] = ptx::pack_bf16x2(x0, x1);
+        lo[e] = ptx::pack_bf16x2(x0 - ptx::bf16lo_to_f32(hi[e]), x1 - ptx::bf16hi_to_f32(hi[e]));
+      } else {
+        hi[e] = ptx::pack_f16x2(x0, x1);
+      }
+    }
+    const uint32_t off = ((cbase + q) ^ (row & 7)) << 4;
+    *reinterpret_cast<uint4*>(rowp + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (C::kSplit) *reinterpret_cast<uint4*>(rowp + C::kAPartBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+template <bool REDUCE>
+__device__ __forceinline__ void sin_cos_of(float z, bool want_cos, float& s, float& c) {
+  const float r = REDUCE ? ptx::reduce_2pi(z) : z;
+  s = ptx::sin_approx(r);
+  c = want_cos ? ptx::cos_approx(r) : 0.f;
+}
+
+__device__ __forceinline__ void stash_store_f16(__half* dst, const float (&c)[32]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) w[e] = ptx::pack_f16x2(c[q * 8 + 2 * e], c[q * 8 + 2 * e + 1]);
+    d4[q] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ------------------------------------------------------------------ forward
+template <int H, int PREC, bool STASH, bool REDUCE>
+__global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
+                                                                const float* __restrict__ coords,
+                                                                int64_t coord_frame_stride,
+                                                                const float* __restrict__ shift,
+                                                                float* __restrict__ out, __half* __restrict__ stash,
+                                                                int64_t T, int64_t P, int num_stages) {
+  using C = TcCfg<H, PREC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_smem = smem;
+  uint8_t* ring = smem + C::kABytes;
+  TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(ring + (size_t)num_stages * kStageBytes);
+
+  const PackedLayout lay = make_layout(d);
+  const int nl = d.nl, cin = d.cin, cout = d.cout;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t PB = (P + kTileM - 1) / kTileM;
+  const int64_t tiles = T * PB;
+  const int64_t SH = (int64_t)(nl + 1) * H;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      ptx::mbar_init(&tail->b_full[s], 1);
+      ptx::mbar_init(&tail->b_empty[s], 1);
+    }
+    ptx::mbar_init(&tail->a_full, 128);
+    ptx::mbar_init(&tail->d_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(&tail->tmem_base, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp < 4) {
+    // ===================== epilogue / activation warps =====================
+    const int row = threadIdx.x;
+    const float* w_first = reinterpret_cast<const float*>(packed + lay.w_first);
+    const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
+    const float* b_out = reinterpret_cast<const float*>(packed + lay.b_out);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t d_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
+      const bool valid = p < P;
+      const float* sh = shift + t * SH;
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        const float* cp = coords + t * coord_frame_stride + p * cin;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < cin) x[j] = cp[j];
+      }
+      __half* st_row = STASH ? stash + (t * P + (valid ? p : 0)) * SH : nullptr;
+
+      // ---- layer 0: K = cin on CUDA cores, always range-reduced (|arg| reaches tens of radians)
+#pragma unroll 1
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        float h[32], cs[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float z = __ldg(sh + c0 + j);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < cin) z = fmaf(__ldg(w_first + (c0 + j) * cin + i), x[i], z);
+          sin_cos_of<true>(z, STASH, h[j], cs[j]);
+        }
+        tc_store_a<H, PREC>(a_smem, row, c0, h);
+        if (STASH && valid) stash_store_f16(st_row + c0, cs);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&tail->a_full);
+
+      float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int l = 1; l <= nl; ++l) {
+        const float* shl = sh + (size_t)l * H;
+        ptx::mbar_wait(&tail->d_full, d_phase);
+        d_phase ^= 1u;
+        ptx::tc_fence_after();
+        const bool last = (l == nl);
+#pragma unroll 1
+        for (int c0 = 0; c0 < H; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tmem_row + c0, v);
+          ptx::tmem_wait_ld();
+          float h[32], cs[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(shl + c0) + q);
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              sin_cos_of<REDUCE>(__uint_as_float(v[q * 4 + e]) + sv[e], STASH, h[q * 4 + e], cs[q * 4 + e]);
+          }
+          if (!last) {
+            tc_store_a<H, PREC>(a_smem, row, c0, h);
+          } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              if (o >= cout) continue;
+              float acc = y[o];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_out + (size_t)o * H + c0) + q);
+                acc = fmaf(w4.x, h[q * 4 + 0], acc);
+                acc = fmaf(w4.y, h[q * 4 + 1], acc);
+                acc = fmaf(w4.z, h[q * 4 + 2], acc);
+                acc = fmaf(w4.w, h[q * 4 + 3], acc);
+              }
+              y[o] = acc;
+            }
+          }
+          if (STASH && valid) stash_store_f16(st_row + (size_t)l * H + c0, cs);
+        }
+        if (!last) {
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&tail->a_full);
+        }
+      }
+      if (valid) {
+        float* op = out + (t * P + p) * cout;
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (o < cout) op[o] = y[o] + __ldg(b_out + o);
+      }
+    }
+    ptx::tc_fence_before();
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
+      int slot = 0;
+      uint32_t b_phase = 0, a_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int l = 1; l <= nl; ++l) {
+          ptx::mbar_wait(&tail->a_full, a_phase);
+          a_phase ^= 1u;
+          ptx::tc_fence_after();
+          tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_base, tail, num_stages, slot, b_phase);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      const uint8_t* wsrc = packed + (C::kSplit ? lay.tc_fwd_x3 : lay.tc_fwd_h);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int l = 0; l < nl; ++l) {
+          const uint8_t* src = wsrc + (size_t)l * C::kStagesPerLayer * kStageBytes;
+          for (int s = 0; s < C::kStagesPerLayer; ++s) {
+            ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kStageBytes);
+            ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
+                          &tail->b_full[slot]);
+            if (++slot == num_stages) { slot = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ backward (to the FiLM shifts)
+// delta_nl = (gout * W_out) .* cos_nl ; for l = nl..1: delta_{l-1} = (delta_l * w0*W_l) .* cos_{l-1};
+// gshift[t, l, n] += sum over the tile's points of delta_l[., n].  Always bf16 hi/lo split operands.
+__device__ __forceinline__ void colsum_to_global(float (&v)[32], int lane, float* dst) {
+  // transpose-reduce: after 5 rounds lane j holds the sum over the warp's 32 rows of column j
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[i] = (upper ? v[i + off] : v[i]) + recv;
+    }
+  }
+  atomicAdd(dst + lane, v[0]);
+}
+
+template <int H>
+__global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_backward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
+                                                                 const float* __restrict__ gout,
+                                                                 const __half* __restrict__ stash,
+                                                                 float* __restrict__ gshift, int64_t T, int64_t P,
+                                                                 int num_stages) {
+  constexpr int PREC = CNF_PREC_BF16X3;
+  using C = TcCfg<H, PREC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_smem = smem;
+  uint8_t* ring = smem + C::kABytes;
+  TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(ring + (size_t)num_stages * kStageBytes);
+
+  const PackedLayout lay = make_layout(d);
+  const int nl = d.nl, cout = d.cout;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t PB = (P + kTileM - 1) / kTileM;
+  const int64_t tiles = T * PB;
+  const int64_t SH = (int64_t)(nl + 1) * H;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      ptx::mbar_init(&tail->b_full[s], 1);
+      ptx::mbar_init(&tail->b_empty[s], 1);
+    }
+    ptx::mbar_init(&tail->a_full, 128);
+    ptx::mbar_init(&tail->d_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(&tail->tmem_base, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp < 4) {
+    const int row = threadIdx.x;
+    const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t d_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
+      const bool valid = p < P;
+      float* gs = gshift + t * SH;
+      const __half* st_row = stash + (t * P + (valid ? p : 0)) * SH;
+      float gy[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (o < cout) gy[o] = gout[(t * P + p) * cout + o];
+      }
+
+      auto load_cos = [&](int l, int c0, float (&c)[32]) {
+        if (valid) {
+          const uint4* s4 = reinterpret_cast<const uint4*>(st_row + (size_t)l * H + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 w = __ldg(s4 + q);
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[e]));
+              c[q * 8 + 2 * e] = f.x;
+              c[q * 8 + 2 * e + 1] = f.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) c[j] = 0.f;
+        }
+      };
+
+      // ---- seed: delta at the last sine layer
+#pragma unroll 1
+      for (int c0 = 0; c0 < H; c0 += 32) {
+        float cs[32], dl[32];
+        load_cos(nl, c0, cs);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float g = 0.f;
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < cout) g = fmaf(gy[o], __ldg(w_out + (size_t)o * H + c0 + j), g);
+          dl[j] = g * cs[j];
+        }
+        tc_store_a<H, PREC>(a_smem, row, c0, dl);
+        colsum_to_global(dl, lane, gs + (size_t)nl * H + c0);
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&tail->a_full);
+
+#pragma unroll 1
+      for (int l = nl; l >= 1; --l) {
+        ptx::mbar_wait(&tail->d_full, d_phase);
+        d_phase ^= 1u;
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < H; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tmem_row + c0, v);
+          float cs[32], dl[32];
+          load_cos(l - 1, c0, cs);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
+          if (l > 1) tc_store_a<H, PREC>(a_smem, row, c0, dl);
+          colsum_to_global(dl, lane, gs + (size_t)(l - 1) * H + c0);
+        }
+        ptx::tc_fence_before();
+        if (l > 1) {
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&tail->a_full);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
+      int slot = 0;
+      uint32_t b_phase = 0, a_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int l = nl; l >= 1; --l) {
+          ptx::mbar_wait(&tail->a_full, a_phase);
+          a_phase ^= 1u;
+          ptx::tc_fence_after();
+          tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_base, tail, num_stages, slot, b_phase);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    if (lane == 0) {
+      const uint8_t* wsrc = packed + lay.tc_bwd_x3;
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int l = nl - 1; l >= 0; --l) {
+          const uint8_t* src = wsrc + (size_t)l * C::kStagesPerLayer * kStageBytes;
+          for (int s = 0; s < C::kStagesPerLayer; ++s) {
+            ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kStageBytes);
+            ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
+                          &tail->b_full[slot]);
+            if (++slot == num_stages) { slot = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+}  // namespace cnf

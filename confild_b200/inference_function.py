@@ -1,0 +1,84 @@
+"""Decode drivers with the reference's signatures (ConditionalNeuralField/cnf/inference_function.py).
+
+``pass_through_model_batch`` (:22-48, grad-enabled, used by the DPS measurement operators) and
+``decoder`` (:51-76, ``no_grad`` + host copy) loop in the reference over ``batch_size`` frames per
+Python iteration, re-upload the coordinates every iteration and, for ``decoder``, synchronise on a
+``.cpu()`` per batch.  Here the same functions issue the frames in large chunks (bounded by an
+output-bytes budget, not by ``batch_size``), normalise the coordinates once, and ``decoder`` streams
+each finished chunk to pinned host memory on a side stream while the next chunk decodes.
+Results are identical to the reference loop's (each frame is independent of how frames are batched).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+#: upper bound of decoded output bytes per kernel launch (frames per chunk follow from it)
+CHUNK_OUTPUT_BYTES = 1 << 30
+
+
+def _frames_per_chunk(t_size: int, m_size: int, cout: int, batch_size: int) -> int:
+    per_frame = max(1, m_size * cout * 4)
+    return max(int(batch_size), min(t_size, CHUNK_OUTPUT_BYTES // per_frame), 1)
+
+
+def _out_features(model) -> int:
+    return int(model.net1[-1].weight.shape[0])
+
+
+def pass_through_model_batch(coords, latents, model, x_normalizer, y_normalizer, batch_size, device):
+    """Grad-enabled decode of ``latents (T, L)`` at ``coords (M, cin)`` -> ``(T, M, cout)``.
+
+    Same contract as the reference (:22-48); gradients flow to ``latents`` through the CUDA
+    backward kernels.
+    """
+    t_size, latent_size = latents.shape
+    m_size, coords_size = coords.shape
+    coords_n = x_normalizer.normalize(coords.reshape(1, m_size, coords_size).to(device))
+    step = _frames_per_chunk(t_size, m_size, _out_features(model), batch_size)
+    outs = []
+    for sid in range(0, t_size, step):
+        batch_latent = latents[sid:sid + step].reshape(-1, 1, latent_size)
+        outs.append(y_normalizer.denormalize(model(coords_n, batch_latent)))
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+
+def decoder(coords, latents, model, x_normalizer, y_normalizer, batch_size, device,
+            out: Optional[torch.Tensor] = None):
+    """``no_grad`` decode returning a HOST tensor ``(T, M, cout)`` like the reference (:51-76).
+
+    Chunks are copied device->host asynchronously into pinned memory (``out`` may be a caller-provided
+    pinned buffer) so the copy of chunk i overlaps the decode of chunk i+1.
+    """
+    t_size, latent_size = latents.shape
+    m_size, coords_size = coords.shape
+    cout = _out_features(model)
+    dev = torch.device(device)
+    step = _frames_per_chunk(t_size, m_size, cout, batch_size)
+    if out is None:
+        out = torch.empty((t_size, m_size, cout), dtype=torch.float32, pin_memory=(dev.type == "cuda"))
+    with torch.no_grad():
+        coords_n = x_normalizer.normalize(coords.reshape(1, m_size, coords_size).to(dev))
+        if dev.type != "cuda":
+            for sid in range(0, t_size, step):
+                lat = latents[sid:sid + step].reshape(-1, 1, latent_size)
+                out[sid:sid + step] = y_normalizer.denormalize(model(coords_n, lat))
+            return out
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        pending = []
+        for sid in range(0, t_size, step):
+            lat = latents[sid:sid + step].reshape(-1, 1, latent_size).to(dev)
+            chunk = y_normalizer.denormalize(model(coords_n, lat))
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                out[sid:sid + chunk.shape[0]].copy_(chunk, non_blocking=True)
+                chunk.record_stream(copy_stream)
+            pending.append(chunk)
+            if len(pending) > 2:  # bound the number of in-flight device chunks
+                pending.pop(0)
+        copy_stream.synchronize()
+    return out

@@ -1,0 +1,128 @@
+/*
+ * confild_cnf.h -- C ABI of the B200-native CNF decode path (libconfild_cnf.so).
+ *
+ * Drop-in boundary for ONE hot path of CoNFiLD: decoding the FiLM-modulated SIREN
+ * auto-decoder, forward and backward-to-latent.  Every entry point replaces a piece
+ * of the reference's PyTorch module (paths relative to the reference checkout):
+ *
+ *   SIRENAutodecoder_film.forward         ConditionalNeuralField/cnf/nf_networks.py:480-495
+ *   BatchLinear.forward                   ConditionalNeuralField/cnf/components.py:64-76
+ *   Sine.forward                          ConditionalNeuralField/cnf/components.py:19-25
+ *   autograd of the above wrt latents     ConditionalDiffusionGeneration/src/guided_diffusion/condition_methods.py:28-33
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross this boundary.
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (PyTorch owns all
+ *     buffers); the library never allocates or frees caller-visible memory.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call
+ *     synchronises the device.  The library keeps no mutable global state except the
+ *     thread-local last-error string.
+ *   - return value: 0 = ok, otherwise a CNF_ERR_* code; cnf_last_error() gives the text.
+ *   - all tensors are fp32, contiguous, row-major unless stated otherwise.
+ *
+ * Notation: cin = coordinate features, L = latent features, H = hidden width,
+ * nl = number of hidden (H x H) layers, cout = output features, T = frames (latents),
+ * P = query points.  w0 is the sine frequency (reference: initialization.py:5).
+ */
+#ifndef CONFILD_CNF_H_
+#define CONFILD_CNF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNF_ABI_VERSION 1
+
+/* error codes */
+#define CNF_OK 0
+#define CNF_ERR_INVALID_ARGUMENT 1 /* null pointer, non-positive size, bad enum            */
+#define CNF_ERR_UNSUPPORTED 2      /* shape/precision combination has no kernel            */
+#define CNF_ERR_CUDA 3             /* a CUDA runtime call or launch failed                 */
+#define CNF_ERR_BUFFER_TOO_SMALL 4 /* caller-provided buffer smaller than cnf_*_bytes said */
+
+/* operand precision of the hidden-layer GEMM chain (accumulation is always fp32) */
+#define CNF_PREC_FP32 0   /* CUDA-core fp32 FMA chain: exact-order reference on the GPU, any H          */
+#define CNF_PREC_BF16X3 1 /* tcgen05, bf16 hi/lo split, 3 MMAs per product (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo) */
+#define CNF_PREC_FP16 2   /* tcgen05, single fp16 MMA per product (fast mode; error ~4e-4..1e-3)          */
+
+typedef struct cnf_dims {
+  int32_t cin;  /* in_coord_features   */
+  int32_t L;    /* in_latent_features  */
+  int32_t H;    /* hidden_features     */
+  int32_t nl;   /* num_hidden_layers   */
+  int32_t cout; /* out_features        */
+} cnf_dims;
+
+/* Library / ABI version and the text of the last error raised on this thread. */
+int cnf_abi_version(void);
+const char* cnf_last_error(void);
+
+/* 1 if the tensor-core (tcgen05) kernels exist for these dims, else 0 (CUDA-core fp32 only). */
+int cnf_tc_supported(const cnf_dims* dims);
+
+/* Number of fp32 elements of the flat parameter vector expected by cnf_pack_weights:
+ * the reference module's state_dict order (nf_networks.py:465-468):
+ *   net1.0.weight (H,cin), net1.0.bias (H), net1.i.weight (H,H), net1.i.bias (H) for i=1..nl,
+ *   net1.{nl+1}.weight (cout,H), net1.{nl+1}.bias (cout), then net2.i.weight (H,L) for i=0..nl. */
+int cnf_param_count(const cnf_dims* dims, size_t* count);
+
+/* Size in bytes of the packed-weight buffer (device) for these dims. */
+int cnf_packed_bytes(const cnf_dims* dims, size_t* bytes);
+
+/* Pack the module parameters into the device layout the kernels read: w0 folded into the
+ * weights and biases, fp32 copies (plain + transposed) for the CUDA-core path and the
+ * FiLM-shift GEMM, and pre-swizzled bf16 hi/lo and fp16 shared-memory images of every
+ * hidden layer (forward and transposed/backward) for the tcgen05 path.
+ * Replaces: the parameter reads inside BatchLinear.forward (components.py:64-71). */
+int cnf_pack_weights(const cnf_dims* dims, const float* d_params_flat, float w0,
+                     void* d_packed, size_t packed_bytes, void* stream);
+
+/* FiLM shift for every layer in one GEMM:
+ *   d_shift[t, l*H + n] = w0 * ( net1[l].bias[n] + sum_k net2[l].weight[n,k] * latents[t,k] )
+ * d_latents (T,L), d_shift (T,(nl+1)*H).  Replaces net2[i](latents) at nf_networks.py:492
+ * and the bias add at components.py:74, for all i at once. */
+int cnf_film_shift(const cnf_dims* dims, const void* d_packed, const float* d_latents, int64_t T,
+                   float* d_shift, void* stream);
+
+/* Bytes of the optional cosine stash written by cnf_forward for a later cnf_backward. */
+int cnf_stash_bytes(const cnf_dims* dims, int precision, int64_t T, int64_t P, size_t* bytes);
+
+/* Decode.  out[t,p,:] = net1[nl+1]( h_nl ),  h_l = sin( w0*W_l h_{l-1} + shift[t,l,:] ),
+ * h_{-1} = coords[p,:].
+ *   d_coords: (P,cin) shared by all frames when coord_frame_stride == 0, else frame t reads
+ *             d_coords + t*coord_frame_stride (elements), e.g. P*cin for a (T,P,cin) tensor.
+ *   d_shift : output of cnf_film_shift for the same T.
+ *   d_out   : (T,P,cout).
+ *   d_stash : NULL for inference; otherwise cnf_stash_bytes() bytes receiving cos(.) of every
+ *             sine argument (fp16 for the tcgen05 precisions, fp32 for CNF_PREC_FP32).
+ * Replaces the layer loop nf_networks.py:491-494. */
+int cnf_forward(const cnf_dims* dims, const void* d_packed, int precision, const float* d_coords,
+                int64_t coord_frame_stride, const float* d_shift, float* d_out, int64_t T, int64_t P,
+                void* d_stash, size_t stash_bytes, void* stream);
+
+/* Backward to the FiLM shifts: given d_gout = dLoss/dout (T,P,cout) and the stash of the
+ * matching cnf_forward call, accumulates d_gshift[t, l*H+n] = sum_p dLoss/d(arg of sine l,n at t,p).
+ * d_gshift (T,(nl+1)*H) is zeroed by this call before accumulation.
+ * Replaces autograd through nf_networks.py:491-494 (condition_methods.py:32). */
+int cnf_backward(const cnf_dims* dims, const void* d_packed, int precision, const float* d_gout,
+                 const void* d_stash, size_t stash_bytes, float* d_gshift, int64_t T, int64_t P,
+                 void* stream);
+
+/* Backward of cnf_film_shift: d_glatents[t,k] = sum_{l,n} d_gshift[t,l*H+n] * w0 * net2[l].weight[n,k].
+ * d_glatents (T,L). */
+int cnf_film_shift_backward(const cnf_dims* dims, const void* d_packed, const float* d_gshift, int64_t T,
+                            float* d_glatents, void* stream);
+
+/* Introspection for the bench / tests: fills up to `n` int64 values:
+ *   [0] SM count of the current device, [1] CTAs launched by cnf_forward for (precision,T,P),
+ *   [2] threads per CTA, [3] dynamic shared memory bytes per CTA, [4] resident CTAs per SM,
+ *   [5] TMEM columns per CTA (0 for the CUDA-core path), [6] points per tile. */
+int cnf_query_launch(const cnf_dims* dims, int precision, int64_t T, int64_t P, int64_t* values, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONFILD_CNF_H_ */

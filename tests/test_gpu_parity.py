@@ -1,0 +1,234 @@
+"""GPU parity: the CUDA path (through the C ABI, via the drop-in module) against the golden fixtures
+and the CPU oracle.  Tolerances are BASELINE.json's: relative L2 <= 1e-3 on decoded fields and
+<= 1e-2 on dL/dlatent for the tensor-core precisions; the fp32 CUDA-core mode is held to 2e-5 / 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+import confild_b200 as cb
+from confild_b200 import _native
+from helpers import GOLDEN_NAMES, golden_inputs, load_golden
+from oracle import cnf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = {"fp32": 2e-5, "bf16x3": 1e-3, "fp16": 1e-3}
+BWD_TOL = {"fp32": 1e-4, "bf16x3": 1e-2, "fp16": 1e-2}
+# what the implementation is expected to reach (regression guard, tighter than the contract)
+FWD_EXPECT = {"fp32": 2e-5, "bf16x3": 1e-4, "fp16": 1e-3}
+
+
+def make_model(dims, sd, precision):
+    cin, L, cout, nl, H = dims
+    m = cb.SIRENAutodecoder_film(cin, L, cout, nl, H, precision=precision)
+    m.load_state_dict(sd)
+    return m.eval().cuda()
+
+
+def precisions_for(dims):
+    d = _native.dims(dims[0], dims[1], dims[4], dims[3], dims[2])
+    return ["fp32", "bf16x3", "fp16"] if _native.tc_supported(d) else ["fp32"]
+
+
+def test_library_loaded_and_device_is_blackwell():
+    _native.load()
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_forward_vs_golden(name):
+    g = load_golden(name)
+    sd, c, l = golden_inputs(g)
+    for prec in precisions_for(g["dims"]):
+        m = make_model(g["dims"], sd, prec)
+        with torch.no_grad():
+            y = m(c.cuda(), l.cuda())
+        assert tuple(y.shape) == g["y"].shape
+        err = O.rel_l2(y, torch.from_numpy(g["y"]))
+        print(f"{name} {prec}: fwd rel_l2 = {err:.3e}")
+        assert err <= FWD_TOL[prec], (name, prec, err)
+        assert err <= FWD_EXPECT[prec], (name, prec, err)
+
+
+@pytest.mark.parametrize("name", [n for n in GOLDEN_NAMES if n != "case1_grid"])
+def test_latent_gradient_vs_golden(name):
+    g = load_golden(name)
+    sd, c, l = golden_inputs(g)
+    mask, y_meas = torch.from_numpy(g["mask"]).cuda(), torch.from_numpy(g["y_meas"]).cuda()
+    for prec in precisions_for(g["dims"]):
+        m = make_model(g["dims"], sd, prec)  # parameters keep requires_grad=True, as in measurements.py
+        lat = l.cuda().requires_grad_(True)
+        y = m(c.cuda(), lat)
+        norm = torch.linalg.norm((y_meas - y) * mask)  # condition_methods.py:30-31
+        (grad,) = torch.autograd.grad(norm, lat)       # condition_methods.py:32
+        assert grad.shape == lat.shape
+        err = O.rel_l2(grad.reshape(g["dlatents"].shape), torch.from_numpy(g["dlatents"]))
+        lerr = abs(float(norm) - float(g["loss"])) / abs(float(g["loss"]))
+        print(f"{name} {prec}: dlat rel_l2 = {err:.3e}, loss rel = {lerr:.3e}")
+        assert err <= BWD_TOL[prec], (name, prec, err)
+        assert lerr <= FWD_TOL[prec]
+
+
+@pytest.mark.parametrize("case,T,P", [("case1", 5, 4099), ("case1", 16, 65536), ("case2", 3, 1500),
+                                      ("case3", 3, 1500), ("case4", 2, 3000)])
+def test_forward_vs_oracle_seeded(case, T, P):
+    """SURVEY.md 7.2 sizes: seeded inputs, oracle on the host cores, all precisions."""
+    dims = O.CASE_SHAPES[case]
+    sd = O.init_params(*dims, seed=0)
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    want = O.forward(sd, coords[None], lat[:, None])
+    for prec in precisions_for(dims):
+        m = make_model(dims, sd, prec)
+        with torch.no_grad():
+            y = m(coords.cuda()[None], lat.cuda()[:, None])
+        err = O.rel_l2(y, want)
+        print(f"{case} T={T} P={P} {prec}: fwd rel_l2 = {err:.3e}")
+        assert err <= FWD_TOL[prec], (case, prec, err)
+
+
+@pytest.mark.parametrize("sigma", [0.0, 1.0])
+def test_forward_latent_scales(sigma):
+    dims = O.CASE_SHAPES["case1"]
+    sd = O.init_params(*dims, seed=0)
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], 4, 1000, sigma=sigma)
+    want = O.forward(sd, coords[None], lat[:, None])
+    for prec in ("bf16x3", "fp16"):
+        m = make_model(dims, sd, prec)
+        with torch.no_grad():
+            err = O.rel_l2(m(coords.cuda()[None], lat.cuda()[:, None]), want)
+        print(f"sigma={sigma} {prec}: {err:.3e}")
+        assert err <= FWD_TOL[prec]
+
+
+@pytest.mark.parametrize("case,T,P,sensors", [("case1", 64, 16384, 1000), ("case4", 8, 2048, 500)])
+def test_dps_gradient_vs_oracle(case, T, P, sensors):
+    """BASELINE config 4: random-sensor mask, dL/dlatent vs autograd on the oracle."""
+    dims = O.CASE_SHAPES[case]
+    sd = O.init_params(*dims, seed=0)
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    rng = np.random.default_rng(0)
+    mask = torch.zeros(P, 1)
+    mask[rng.choice(P, sensors, replace=False)] = 1.0
+    y_meas = torch.randn(T, P, dims[2], generator=torch.Generator().manual_seed(3)) * 0.05
+    loss_ref, _, g_ref = O.grad_latents(sd, coords[None], lat[:, None], lambda y: O.sensor_loss(y, y_meas, mask))
+    for prec in precisions_for(dims):
+        m = make_model(dims, sd, prec)
+        latg = lat.cuda()[:, None].requires_grad_(True)
+        y = m(coords.cuda()[None], latg)
+        loss = torch.linalg.norm((y_meas.cuda() - y) * mask.cuda())
+        (g,) = torch.autograd.grad(loss, latg)
+        err = O.rel_l2(g, g_ref)
+        print(f"{case} DPS {prec}: dlat rel_l2 = {err:.3e} loss {float(loss):.6f} vs {float(loss_ref):.6f}")
+        assert err <= BWD_TOL[prec], (case, prec, err)
+
+
+def test_edge_shapes_and_batch_invariance():
+    dims = O.CASE_SHAPES["case1"]
+    sd = O.init_params(*dims, seed=0)
+    m = make_model(dims, sd, "bf16x3")
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], 9, 333)
+    c, l = coords.cuda(), lat.cuda()
+    with torch.no_grad():
+        full = m(c[None], l[:, None])
+        # T = 1, P = 1, P not a multiple of 128, empty inputs
+        one = m(c[None, :1], l[:1, None])
+        assert torch.equal(one[0, 0], full[0, 0])
+        assert m(c[None, :0], l[:, None]).shape == (9, 0, 3)
+        assert m(c[None], l[:0, None]).shape == (0, 333, 3)
+        # frames are independent of how they are batched (reference loops over batches of 16 / 1)
+        parts = torch.cat([m(c[None], l[i:i + 2, None]) for i in range(0, 9, 2)])
+        assert torch.equal(parts, full)
+        # points are independent of their tile: a permutation of the points permutes the output
+        perm = torch.randperm(333, device="cuda")
+        assert torch.equal(m(c[None, perm], l[:, None]), full[:, perm])
+        # per-frame coords equal shared coords when every frame carries the same points
+        assert torch.equal(m(c[None].expand(9, 333, 2).contiguous(), l[:, None]), full)
+
+
+def test_repack_on_weight_change_and_w0():
+    dims = O.CASE_SHAPES["case1"]
+    sd = O.init_params(*dims, seed=0)
+    m = make_model(dims, sd, "bf16x3")
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], 2, 200)
+    c, l = coords.cuda()[None], lat.cuda()[:, None]
+    with torch.no_grad():
+        y0 = m(c, l)
+        sd2 = O.init_params(*dims, seed=1)
+        m.load_state_dict(sd2)
+        y1 = m(c, l)
+    assert O.rel_l2(y1, O.forward(sd2, coords[None], lat[:, None])) < 1e-4
+    assert not torch.equal(y0, y1)
+    try:
+        m.nl.w0 = 20.0  # the reference's shared Sine instance is mutable; w0 is read at call time
+        with torch.no_grad():
+            y2 = m(c, l)
+        assert O.rel_l2(y2, O.forward(sd2, coords[None], lat[:, None], w0=20.0)) < 1e-4
+    finally:
+        m.nl.w0 = 30.0
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size (case1, T=1024, P=65536): tensor-core result against the fp32
+    CUDA-core chain on every frame of a strided subset, plus oracle spot checks on the host."""
+    dims = O.CASE_SHAPES["case1"]
+    sd = O.init_params(*dims, seed=0)
+    T, P = 1024, 65536
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    c, l = coords.cuda()[None], lat.cuda()[:, None]
+    m = make_model(dims, sd, "bf16x3")
+    with torch.no_grad():
+        y = m(c, l)
+    assert y.shape == (T, P, 3) and bool(torch.isfinite(y).all())
+    m32 = make_model(dims, sd, "fp32")
+    frames = torch.arange(0, T, 64, device="cuda")
+    with torch.no_grad():
+        y32 = m32(c, l[frames])
+    err = O.rel_l2(y[frames], y32)
+    print(f"config2 full size: bf16x3 vs fp32 chain on {len(frames)} frames: {err:.3e}")
+    assert err <= 1e-4
+    pts = torch.arange(17, P, 4099)
+    want = O.forward(sd, coords[None, pts], lat[frames.cpu(), None])
+    got = y[frames][:, pts.cuda()]
+    assert O.rel_l2(got, want) <= 1e-4
+    # a frame decoded alone equals the same frame inside the 1024-frame launch
+    with torch.no_grad():
+        assert torch.equal(m(c, l[1000:1001]), y[1000:1001])
+
+
+def test_reference_callers_shapes():
+    """trainer.infer / CNF_inference.predict / pass_through_model_batch call patterns."""
+    dims = O.CASE_SHAPES["case1"]
+    sd = O.init_params(*dims, seed=0)
+    m = make_model(dims, sd, "bf16x3")
+    g = torch.Generator().manual_seed(5)
+    grid = torch.rand(12, 20, 2, generator=g) * 2 - 1
+    lat = torch.randn(3, 128, generator=g) * 0.1
+    with torch.no_grad():
+        y = m(grid.cuda(), lat.cuda()[:, None, None])      # predict: (B,1,1,L) x (h,w,cin)
+    assert y.shape == (3, 12, 20, 3)
+    assert O.rel_l2(y, O.forward(sd, grid, lat[:, None, None])) < 1e-4
+
+    class N:  # '-11' normaliser, normalize.py:100-120
+        def __init__(self, hi, lo):
+            self.hi, self.lo = hi, lo
+
+        def normalize(self, x):
+            return (x - self.lo.to(x.device)) / (self.hi.to(x.device) - self.lo.to(x.device)) * 2 - 1
+
+        def denormalize(self, y):
+            return (y + 1) / 2 * (self.hi.to(y.device) - self.lo.to(y.device)) + self.lo.to(y.device)
+
+    xn, yn = N(torch.tensor([2.0, 3.0]), torch.tensor([-1.0, 0.5])), N(torch.tensor([1.0, 2.0, 3.0]), torch.tensor([-1.0, -2.0, 0.0]))
+    coords = torch.rand(500, 2, generator=g) * torch.tensor([3.0, 2.5]) + torch.tensor([-1.0, 0.5])
+    lat = torch.randn(37, 128, generator=g) * 0.1
+    want = yn.denormalize(O.forward(sd, xn.normalize(coords)[None], lat[:, None]))
+    got = cb.pass_through_model_batch(coords.cuda(), lat.cuda(), m, xn, yn, 16, "cuda")
+    assert got.shape == (37, 500, 3) and O.rel_l2(got, want) < 1e-4
+    host = cb.decoder(coords, lat.cuda(), m, xn, yn, 16, "cuda")
+    assert host.device.type == "cpu" and O.rel_l2(host, want) < 1e-4
+
+
+def test_training_mode_with_grad_raises():
+    m = cb.SIRENAutodecoder_film(2, 128, 3, 10, 128).cuda()  # training mode, params require grad
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 4, 2, device="cuda"), torch.zeros(2, 1, 128, device="cuda", requires_grad=True))

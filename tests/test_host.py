@@ -1,0 +1,122 @@
+"""CPU: host-side logic of the drop-in module (no kernels are launched here)."""
+import torch
+import pytest
+
+import confild_b200 as cb
+from confild_b200.nf_networks import canonicalize
+from oracle import cnf_oracle as O
+
+
+def test_state_dict_layout_and_init_match_reference_order():
+    torch.manual_seed(0)
+    m = cb.SIRENAutodecoder_film(2, 128, 3, 10, 128)
+    sd = O.init_params(2, 128, 3, 10, 128, seed=0)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    assert m.nl.w0 == 30.0
+    assert len(m.net1) == 12 and len(m.net2) == 11
+
+
+def test_positional_and_keyword_construction():
+    a = cb.SIRENAutodecoder_film(3, 384, 3, 15, 384)  # measurements.py:207 style
+    b = cb.SIRENAutodecoder_film(in_coord_features=3, in_latent_features=384, out_features=3,
+                                 num_hidden_layers=15, hidden_features=384)  # scripts/train.py:230-236 style
+    assert a._dims_tuple == b._dims_tuple == (3, 384, 384, 15, 3)
+    b.load_state_dict(a.state_dict())
+    a.disable_gradient()
+    assert not any(p.requires_grad for p in a.parameters())
+
+
+def test_unsupported_configs_raise():
+    with pytest.raises(NotImplementedError):
+        cb.SIRENAutodecoder_film(2, 8, 3, 1, 16, premap_mode="fourier")
+    with pytest.raises(NotImplementedError):
+        cb.SIRENAutodecoder_film(2, 8, 3, 1, 16, nonlinearity="relu")
+
+
+def test_cpu_forward_fails_loudly():
+    m = cb.SIRENAutodecoder_film(2, 8, 3, 1, 16).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 5, 2), torch.zeros(3, 1, 8))
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 5, 3), torch.zeros(3, 1, 8))
+    with pytest.raises(TypeError):
+        m(torch.zeros(1, 5, 2, dtype=torch.float64), torch.zeros(3, 1, 8))
+
+
+@pytest.mark.parametrize("cshape,lshape,T,P,stride", [
+    ((1, 50, 2), (7, 1, 8), 7, 50, 0),         # pass_through_model_batch
+    ((50, 2), (7, 1, 8), 7, 50, 0),            # trainer.infer, flat coords
+    ((5, 6, 2), (7, 1, 1, 8), 7, 30, 0),       # CNF_inference.predict, grid coords
+    ((7, 50, 2), (7, 1, 8), 7, 50, 100),       # training loop, per-frame coords
+    ((50, 2), (8,), 1, 50, 0),                 # single latent vector
+    ((4, 50, 2), (50, 8), 200, 1, 2),          # latents varying per point: every pair is its own frame
+])
+def test_canonicalize_matches_broadcast(cshape, lshape, T, P, stride):
+    g = torch.Generator().manual_seed(0)
+    c = torch.rand(cshape, generator=g)
+    l = torch.rand(lshape, generator=g)
+    cc, st, l2, T_, P_, lead = canonicalize(c, l)
+    assert (T_, P_, st) == (T, P, stride)
+    assert tuple(l2.shape) == (T, 8)
+    # rebuild the broadcast operands from the canonical form and compare with torch broadcasting
+    cfull = (cc[None].expand(T, P, 2) if st == 0 else cc).reshape(lead + (2,))
+    lfull = l2[:, None, :].expand(T, P, 8).reshape(lead + (8,))
+    assert torch.equal(cfull, c.expand(lead + (2,)))
+    assert torch.equal(lfull, l.expand(lead + (8,)))
+
+
+def test_canonicalize_keeps_latent_grad_path():
+    l = torch.rand(3, 1, 8, requires_grad=True)
+    _, _, l2, *_ = canonicalize(torch.rand(1, 5, 2), l)
+    (g,) = torch.autograd.grad(l2.sum(), l)
+    assert tuple(g.shape) == (3, 1, 8) and torch.all(g == 1)
+
+
+def test_install_patches_named_modules():
+    import types
+
+    fake = types.ModuleType("fake.cnf.nf_networks")
+    fake.SIRENAutodecoder_film = object
+    fake.SIRENAutodecoder_film_extra_in = object
+    assert cb.install(fake) == ["fake.cnf.nf_networks"]
+    assert fake.SIRENAutodecoder_film is cb.SIRENAutodecoder_film
+    assert fake.SIRENAutodecoder_film_extra_in is cb.SIRENAutodecoder_film_extra_in
+
+
+class _OracleModel(torch.nn.Module):
+    """Stand-in decode model for driver tests on CPU (checker only)."""
+
+    def __init__(self, sd):
+        super().__init__()
+        self.sd = sd
+        self.net1 = torch.nn.ModuleList([torch.nn.Linear(1, 1) for _ in range(O.dims_of(sd)[3] + 2)])
+        self.net1[-1].weight = torch.nn.Parameter(sd[f"net1.{len(self.net1) - 1}.weight"].clone())
+
+    def forward(self, coords, latents):
+        return O.forward(self.sd, coords, latents)
+
+
+class _Affine:
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+
+    def normalize(self, x):
+        return x * self.a + self.b
+
+    def denormalize(self, y):
+        return (y - self.b) / self.a
+
+
+def test_decode_drivers_equal_reference_loop():
+    sd = O.init_params(2, 16, 3, 2, 32, seed=0)
+    model = _OracleModel(sd)
+    coords, lat = O.synthetic_inputs(2, 16, 11, 37)
+    xn, yn = _Affine(0.5, 0.1), _Affine(2.0, -0.3)
+    want = torch.cat([yn.denormalize(O.forward(sd, xn.normalize(coords[None]), lat[i:i + 4, None]))
+                      for i in range(0, 11, 4)])  # the reference's loop, batch_size 4
+    got = cb.pass_through_model_batch(coords, lat, model, xn, yn, 4, "cpu")
+    assert torch.allclose(got, want, atol=1e-6)
+    got2 = cb.decoder(coords, lat, model, xn, yn, 4, "cpu")
+    assert torch.allclose(got2, want, atol=1e-6) and got2.device.type == "cpu"
