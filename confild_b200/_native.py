@@ -33,7 +33,7 @@ _lib: Optional[ctypes.CDLL] = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    return os.environ.get("CONFILD_CNF_LIB", _build.LIB_PATH)
 
 
 def load() -> ctypes.CDLL:

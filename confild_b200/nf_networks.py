@@ -174,6 +174,7 @@ class SIRENAutodecoder_film(nn.Module):
                             int(num_hidden_layers), int(out_features))
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
+        self._timing = None
 
     # ------------------------------------------------------------------ reference API
     def disable_gradient(self):
@@ -272,9 +273,16 @@ class SIRENAutodecoder_film(nn.Module):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _native.check(lib.cnf_film_shift(d, packed.data_ptr(), lat2d.data_ptr(), T, shift.data_ptr(), stream),
                           "cnf_film_shift")
+            timing = getattr(self, "_timing", None)  # bench.py: CUDA events around the chain kernel alone
+            if timing is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             _native.check(lib.cnf_forward(d, packed.data_ptr(), prec, coords_c.data_ptr(), frame_stride,
                                           shift.data_ptr(), out.data_ptr(), T, P, stash_ptr, stash_n, stream),
                           "cnf_forward")
+            if timing is not None:
+                e1.record()
+                timing.append((e0, e1))
         return out, stash
 
     def _launch_backward(self, gout, stash, packed, prec, T, P) -> torch.Tensor:
