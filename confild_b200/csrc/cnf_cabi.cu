@@ -10,6 +10,7 @@
 #include "pack.cuh"
 #include "simt.cuh"
 #include "tc_kernels.cuh"
+#include "tc2_kernels.cuh"
 
 namespace {
 
@@ -140,6 +141,47 @@ int dispatch_tc_forward_h(const cnf_dims& d, const uint8_t* packed, const float*
   return fail(CNF_ERR_UNSUPPORTED, "no tensor-core kernel for H=%d", d.H);
 }
 
+// H = 128 fast path (activations in TMEM, two tiles in flight, one CTA per SM).
+bool use_tc2(const cnf_dims& d, bool stash) { return d.H == cnf::kTc2H && !stash && env_int("CNF_TC2", 1) != 0; }
+
+int make_tc2_plan(const DeviceInfo& di, int64_t tiles, TcPlan* plan) {
+  const size_t fixed = cnf::tc2_smem_bytes(0);
+  int stages = (int)(((size_t)di.max_smem_optin - fixed) / cnf::kStageBytes);
+  if (stages > cnf::kTcMaxStages) stages = cnf::kTcMaxStages;
+  const int forced = env_int("CNF_TC_STAGES", 0);
+  if (forced >= 4 && forced <= stages) stages = forced;
+  if (stages < 6) return fail(CNF_ERR_UNSUPPORTED, "not enough shared memory for the weight ring");
+  plan->stages = stages;
+  plan->ctas_per_sm = 1;
+  plan->smem = cnf::tc2_smem_bytes(stages);
+  plan->tmem_cols = 512;
+  const int64_t pairs = (tiles + 1) / 2;
+  plan->grid = pairs < di.sms ? pairs : di.sms;
+  return CNF_OK;
+}
+
+template <int PREC, bool REDUCE>
+int launch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs, const float* shift,
+                       float* out, int64_t T, int64_t P, cudaStream_t st) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
+  TcPlan plan;
+  if (int rc = make_tc2_plan(di, tiles, &plan)) return rc;
+  auto kern = cnf::tc2_forward_kernel<PREC, REDUCE>;
+  CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  kern<<<(unsigned)plan.grid, cnf::kTc2Threads, plan.smem, st>>>(d, packed, coords, cfs, shift, out, T, P, plan.stages);
+  CNF_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+template <int PREC>
+int dispatch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs,
+                         const float* shift, float* out, int64_t T, int64_t P, cudaStream_t st) {
+  return env_int("CNF_TC_REDUCE", 1) != 0 ? launch_tc2_forward<PREC, true>(d, packed, coords, cfs, shift, out, T, P, st)
+                                           : launch_tc2_forward<PREC, false>(d, packed, coords, cfs, shift, out, T, P, st);
+}
+
 template <int H>
 int launch_tc_backward(const cnf_dims& d, const uint8_t* packed, const float* gout, const void* stash, float* gshift,
                        int64_t T, int64_t P, cudaStream_t st) {
@@ -162,6 +204,13 @@ int64_t simt_grid(int64_t tiles, int sms) {
 }
 
 }  // namespace
+
+#ifdef CNF_TRACE
+extern "C" int cnf_debug_set_trace(void* d_buf) {
+  unsigned long long* p = static_cast<unsigned long long*>(d_buf);
+  return cudaMemcpyToSymbol(cnf::g_trace, &p, sizeof(p)) == cudaSuccess ? 0 : 3;
+}
+#endif
 
 extern "C" {
 
@@ -295,6 +344,11 @@ int cnf_forward(const cnf_dims* dims, const void* d_packed, int precision, const
                 "tensor-core path needs H in {128,256,384}, nl>=1, cin<=4, cout<=4 (got H=%d nl=%d cin=%d cout=%d); "
                 "use CNF_PREC_FP32",
                 dims->H, dims->nl, dims->cin, dims->cout);
+  if (use_tc2(*dims, d_stash != nullptr)) {
+    return precision == CNF_PREC_BF16X3
+               ? dispatch_tc2_forward<CNF_PREC_BF16X3>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out, T, P, st)
+               : dispatch_tc2_forward<CNF_PREC_FP16>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out, T, P, st);
+  }
   if (precision == CNF_PREC_BF16X3)
     return dispatch_tc_forward_h<CNF_PREC_BF16X3>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out, d_stash,
                                                   T, P, st);
@@ -358,6 +412,12 @@ int cnf_query_launch(const cnf_dims* dims, int precision, int64_t T, int64_t P, 
     TcPlan plan;
     int rc = CNF_ERR_UNSUPPORTED;
     const bool x3 = precision == CNF_PREC_BF16X3;
+    if (use_tc2(*dims, false)) {
+      if (int rc2 = make_tc2_plan(di, tiles, &plan)) return rc2;
+      const int64_t v2[7] = {di.sms, plan.grid, cnf::kTc2Threads, (int64_t)plan.smem, 1, 512, 2 * cnf::kTileM};
+      for (int i = 0; i < n && i < 7; ++i) values[i] = v2[i];
+      return CNF_OK;
+    }
     switch (dims->H) {
       case 128: rc = x3 ? make_tc_plan<128, CNF_PREC_BF16X3>(di, tiles, &plan) : make_tc_plan<128, CNF_PREC_FP16>(di, tiles, &plan); break;
       case 256: rc = x3 ? make_tc_plan<256, CNF_PREC_BF16X3>(di, tiles, &plan) : make_tc_plan<256, CNF_PREC_FP16>(di, tiles, &plan); break;

@@ -1,0 +1,341 @@
+// H = 128 fast path of the forward chain: activations never leave tensor memory.
+//
+// One persistent CTA per SM keeps TWO 128-point tiles in flight.  TMEM (512 columns) holds, per tile slot g:
+//   D   fp32 accumulator, 128 columns            [g*256      , +128)
+//   A   next layer's operand, 16-bit packed      [g*256 + 128, +64)  (hi, or the fp16 copy)
+//                                                [g*256 + 192, +64)  (lo of the bf16 split)
+// so the MMA reads A from TMEM (tcgen05.mma with a TMEM A operand) and shared memory is left to the
+// weights: a 12-deep ring of 16 KiB stages (three whole layers of bf16 hi/lo) streamed once per tile PAIR.
+//   warps 0-3 / 4-7  activation warpgroup of slot 0 / 1: tcgen05.ld D -> +FiLM shift -> MUFU sin -> bf16 hi/lo
+//                    (or fp16) -> tcgen05.st A; last layer: output head in registers.
+//   warp 8           one thread issues the MMAs, alternating slots: MMA(slot 0, layer l) runs while warpgroup 1
+//                    is still in its epilogue of layer l-1 and vice versa.
+//   warp 9           one thread streams weight stages with cp.async.bulk (1-D TMA).
+// Each weight stage is consumed by slot 0 then slot 1 before it is released (M = 256 rows per byte fetched from L2).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "layout.cuh"
+#include "ptx.cuh"
+#include "tc_kernels.cuh"
+
+namespace cnf {
+
+#ifdef CNF_TRACE
+// Debug build only: per-role event trace of CTA 0 (role r writes (code, clock64) pairs at trace[r*8192 + 2*n]).
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_event(int role, int& n, unsigned long long code) {
+  if (g_trace != nullptr && blockIdx.x == 0 && n < 4000) {
+    g_trace[role * 8192 + 2 * n] = code;
+    g_trace[role * 8192 + 2 * n + 1] = clock64();
+    ++n;
+  }
+}
+#define CNF_TRACE_DECL int trace_n = 0
+#define CNF_TRACE_EVENT(role, code) trace_event(role, trace_n, code)
+#else
+#define CNF_TRACE_DECL
+#define CNF_TRACE_EVENT(role, code)
+#endif
+
+constexpr int kTc2H = 128;
+constexpr int kTc2EpiWarps = 16;                       // 2 tile slots x 2 column halves x 4 lane quarters
+constexpr int kTc2Threads = (kTc2EpiWarps + 2) * 32;   // + MMA issuer warp + weight producer warp
+constexpr int kTc2SlotCols = 256;
+
+struct Tc2SmemTail {
+  float shift_s[2][2][kTc2H];   // [slot][layer parity][column]
+  float y_part[2][kTileM][4];   // head partial sums of the upper column half, per slot
+  float w_first_s[kTc2H * 4];
+  float w_out_s[4 * kTc2H];
+  uint64_t b_full[kTcMaxStages];
+  uint64_t b_empty[kTcMaxStages];
+  uint64_t a_full[2];
+  uint64_t d_full[2];
+  uint32_t tmem_base;
+};
+
+__host__ __device__ constexpr size_t tc2_smem_bytes(int num_stages) {
+  return 1024 + (size_t)num_stages * kStageBytes + sizeof(Tc2SmemTail);
+}
+
+template <int PREC>
+__device__ __forceinline__ void tc2_store_a(uint32_t tmem_a, int c0, const float (&h)[32]) {
+  constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float x0 = h[2 * e], x1 = h[2 * e + 1];
+    if (kSplit) {
+      hi[e] = ptx::pack_bf16x2(x0, x1);
+      lo[e] = ptx::pack_bf16x2(x0 - ptx::bf16lo_to_f32(hi[e]), x1 - ptx::bf16hi_to_f32(hi[e]));
+    } else {
+      hi[e] = ptx::pack_f16x2(x0, x1);
+    }
+  }
+  ptx::tmem_st_32x32b_x16(tmem_a + c0 / 2, hi);
+  if (kSplit) ptx::tmem_st_32x32b_x16(tmem_a + 64 + c0 / 2, lo);
+}
+
+template <int PREC, bool REDUCE>
+__global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
+                                                                     const float* __restrict__ coords,
+                                                                     int64_t coord_frame_stride,
+                                                                     const float* __restrict__ shift,
+                                                                     float* __restrict__ out, int64_t T, int64_t P,
+                                                                     int num_stages) {
+  constexpr int H = kTc2H;
+  constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
+  constexpr int kParts = kSplit ? 2 : 1;
+  constexpr int kSPL = (H / kSlabK) * kParts;  // stages per layer: 4 (split) or 2
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, H);
+  constexpr int kMmaWarp = kTc2EpiWarps;  // the warp after it is the weight producer
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  Tc2SmemTail* tail = reinterpret_cast<Tc2SmemTail*>(ring + (size_t)num_stages * kStageBytes);
+
+  const PackedLayout lay = make_layout(d);
+  const int nl = d.nl, cin = d.cin, cout = d.cout;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t PB = (P + kTileM - 1) / kTileM;
+  const int64_t tiles = T * PB;
+  const int64_t pairs = (tiles + 1) / 2;
+  const int64_t SH = (int64_t)(nl + 1) * H;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      ptx::mbar_init(&tail->b_full[s], 1);
+      ptx::mbar_init(&tail->b_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(&tail->a_full[g], 256);
+      ptx::mbar_init(&tail->d_full[g], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  {  // small fp32 operands of layer 0 and of the head, once per CTA
+    const float* w_first = reinterpret_cast<const float*>(packed + lay.w_first);
+    const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
+    for (int i = threadIdx.x; i < H * cin; i += kTc2Threads) tail->w_first_s[i] = w_first[i];
+    for (int i = threadIdx.x; i < cout * H; i += kTc2Threads) tail->w_out_s[i] = w_out[i];
+  }
+  if (warp == kMmaWarp) {
+    ptx::tmem_alloc(&tail->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp < kTc2EpiWarps) {
+    // ===================== activation warpgroups =====================
+    // warpgroup (g, hf): tile slot g, columns [64*hf, 64*hf + 64); thread = TMEM lane / query point `row`.
+    const int g = warp / 8, hf = (warp / 4) & 1, wq = warp % 4;
+    const int row = wq * 32 + lane;
+    const int col0 = 64 * hf;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + g * kTc2SlotCols;
+    const uint32_t tmem_a = lane_base + 128;
+    const float* b_out = reinterpret_cast<const float*>(packed + lay.b_out);
+    const uint32_t bar_wg = 1 + g * 2 + hf;  // named barrier of this warpgroup (128 threads)
+    const uint32_t bar_slot = 5 + g;         // named barrier of the slot's two warpgroups (256 threads)
+    uint32_t d_phase = 0;
+    CNF_TRACE_DECL;
+    const bool tracer = (wq == 0 && lane == 0);
+    [[maybe_unused]] const int trole = hf == 0 ? g : 4 + g;
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + g;
+      if (tile >= tiles) continue;
+      const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
+      const bool valid = p < P;
+      const float* sh = shift + t * SH;
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        const float* cp = coords + t * coord_frame_stride + p * cin;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < cin) x[j] = cp[j];
+      }
+      if (tracer) CNF_TRACE_EVENT(trole, 100);  // tile start
+      ptx::bar_sync(bar_wg, 128);           // everyone is done with the previous tile's shift buffers
+      if (wq < 2) tail->shift_s[g][0][col0 + row] = __ldg(sh + col0 + row);
+      ptx::bar_sync(bar_wg, 128);
+
+      // ---- layer 0 on CUDA cores (K = cin), always range-reduced
+#pragma unroll 1
+      for (int c0 = col0; c0 < col0 + 64; c0 += 32) {
+        float h[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float z = tail->shift_s[g][0][c0 + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < cin) z = fmaf(tail->w_first_s[(c0 + j) * cin + i], x[i], z);
+          h[j] = ptx::sin_approx(ptx::reduce_2pi(z));
+        }
+        tc2_store_a<PREC>(tmem_a, c0, h);
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tail->a_full[g]);
+      if (tracer) CNF_TRACE_EVENT(trole, 101);  // layer 0 done, a_full arrived
+
+      float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int l = 1; l <= nl; ++l) {
+        float* sbuf = tail->shift_s[g][l & 1];
+        if (wq < 2) sbuf[col0 + row] = __ldg(sh + (size_t)l * H + col0 + row);
+        ptx::bar_sync(bar_wg, 128);
+        if (tracer) CNF_TRACE_EVENT(trole, 200 + l);  // start waiting for d_full
+        // one warp of the slot polls the mbarrier; the other seven sleep on the hardware barrier (no issue slots)
+        if (hf == 0 && wq == 0) ptx::mbar_wait(&tail->d_full[g], d_phase);
+        d_phase ^= 1u;
+        ptx::bar_sync(bar_slot, 256);
+        ptx::tc_fence_after();
+        if (tracer) CNF_TRACE_EVENT(trole, 300 + l);  // d_full observed
+        const bool last = (l == nl);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int c0 = col0 + c * 32;
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(lane_base + c0, v);
+          ptx::tmem_wait_ld();
+          float h[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sbuf + c0 + q * 4);
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float z = __uint_as_float(v[q * 4 + e]) + sv[e];
+              h[q * 4 + e] = ptx::sin_approx(REDUCE ? ptx::reduce_2pi(z) : z);
+            }
+          }
+          if (!last) {
+            tc2_store_a<PREC>(tmem_a, c0, h);
+          } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              if (o >= cout) continue;
+              float acc = y[o];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4*>(tail->w_out_s + o * H + c0 + q * 4);
+                acc = fmaf(w4.x, h[q * 4 + 0], acc);
+                acc = fmaf(w4.y, h[q * 4 + 1], acc);
+                acc = fmaf(w4.z, h[q * 4 + 2], acc);
+                acc = fmaf(w4.w, h[q * 4 + 3], acc);
+              }
+              y[o] = acc;
+            }
+          }
+        }
+        if (!last) {
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tail->a_full[g]);
+        }
+        if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
+      }
+      // ---- head: combine the two column halves, 12-byte store per point
+      ptx::tc_fence_before();
+      if (hf == 1) *reinterpret_cast<float4*>(tail->y_part[g][row]) = make_float4(y[0], y[1], y[2], y[3]);
+      ptx::bar_sync(bar_slot, 256);
+      if (hf == 0 && valid) {
+        const float4 yp = *reinterpret_cast<const float4*>(tail->y_part[g][row]);
+        const float ys[4] = {y[0] + yp.x, y[1] + yp.y, y[2] + yp.z, y[3] + yp.w};
+        float* op = out + (t * P + p) * cout;
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (o < cout) op[o] = ys[o] + __ldg(b_out + o);
+      }
+    }
+    ptx::tc_fence_before();
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer =====================
+    // The whole warp walks the (uniform) schedule and polls the barriers; one elected lane issues.  Keeping the
+    // control flow converged keeps every tcgen05 operand in uniform registers: the issue loop must sustain one
+    // UTCHMMA per ~64-85 clk, which a divergent single-lane loop (R2UR moves + waterfall loop per MMA) cannot.
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t ring_addr = ptx::smem_u32(ring);
+    uint32_t a_phase0 = 0u, a_phase1 = 0u;
+    int slot0 = 0;         // ring slot of stage 0 of the current layer
+    uint32_t phase0 = 0;   // its mbarrier parity
+    CNF_TRACE_DECL;
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      const int nvalid = (2 * pair + 1 < tiles) ? 2 : 1;
+      for (int l = 1; l <= nl; ++l) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (g < nvalid) {
+            if (lane == 0) CNF_TRACE_EVENT(2, 1000 + g * 100 + l);  // start waiting a_full[g]
+            ptx::mbar_wait(&tail->a_full[g], g == 0 ? a_phase0 : a_phase1);
+            if (g == 0) a_phase0 ^= 1u; else a_phase1 ^= 1u;
+            ptx::tc_fence_after();
+            if (lane == 0) CNF_TRACE_EVENT(2, 2000 + g * 100 + l);  // a_full observed
+            const uint32_t tmem_d = tmem_u + g * kTc2SlotCols;
+            const uint32_t tmem_a = tmem_d + 128;
+            int slot = slot0;
+            uint32_t ph = phase0;
+#pragma unroll
+            for (int s = 0; s < kSPL; ++s) {
+              if (g == 0) {  // first use of the stage: its bytes must have landed
+                ptx::mbar_wait(&tail->b_full[slot], ph);
+                ptx::tc_fence_after();
+              }
+              const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+              const int ks = s / kParts, part = s % kParts;
+              if (ptx::elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint32_t a_hi = tmem_a + (ks * 4 + kk) * 8;  // 16 K elements = 8 packed columns
+                  if (part == 0) {
+                    ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (ks | kk) != 0);
+                    if (kSplit) ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
+                  } else {
+                    ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
+                  }
+                }
+                if (g == nvalid - 1) ptx::umma_commit(&tail->b_empty[slot]);  // last reader frees the stage
+                if (s == kSPL - 1) ptx::umma_commit(&tail->d_full[g]);
+              }
+              __syncwarp();
+              if (++slot == num_stages) { slot = 0; ph ^= 1u; }
+            }
+            if (lane == 0) CNF_TRACE_EVENT(2, 3000 + g * 100 + l);  // all MMAs of (g,l) issued + committed
+          }
+        }
+        slot0 += kSPL;
+        if (slot0 >= num_stages) { slot0 -= num_stages; phase0 ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      const uint8_t* wsrc = packed + (kSplit ? lay.tc_fwd_x3 : lay.tc_fwd_h);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+        for (int l = 0; l < nl; ++l) {
+          const uint8_t* src = wsrc + (size_t)l * kSPL * kStageBytes;
+          for (int s = 0; s < kSPL; ++s) {
+            ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kStageBytes);
+            ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
+                          &tail->b_full[slot]);
+            if (++slot == num_stages) { slot = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace cnf

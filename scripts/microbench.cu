@@ -1,0 +1,237 @@
+// Micro-benchmarks that size the CNF forward kernel on B200 (sm_100a): tcgen05.mma issue pace with the A operand in
+// shared memory vs tensor memory, tcgen05.ld / tcgen05.st throughput, their interference, and MUFU.SIN throughput.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I confild_b200/csrc scripts/microbench.cu -o scripts/microbench
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "ptx.cuh"
+
+using namespace cnf;
+
+struct Tail {
+  uint64_t bar_mma[2];
+  uint32_t tmem_base;
+};
+
+// flags: bit0 = run MMAs, bit1 = MMA A operand from TMEM, bit2 = run LDTM loops (warps 0-3), bit3 = also STTM,
+//        bit4 = LDTM warps 4-7 too (second slot)
+__global__ void __launch_bounds__(320, 1) mb_tensor(int flags, int groups, int mma_per_group, int n_dim,
+                                                    unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  Tail* tail = reinterpret_cast<Tail*>(smem + 64 * 1024);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int i = threadIdx.x; i < 16 * 1024; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&tail->bar_mma[0], 1);
+    ptx::mbar_init(&tail->bar_mma[1], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) {
+    ptx::tmem_alloc(&tail->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+  const bool do_mma = flags & 1, a_tmem = flags & 2, do_ld = flags & 4, do_st = flags & 8, ld2 = flags & 16;
+  const bool alt_d = flags & 32, no_acc = flags & 64;
+  unsigned long long t0 = 0, t1 = 0;
+  if (warp < 8) {
+    if (do_ld && (warp < 4 || ld2)) {
+      const int wq = warp % 4, g = warp / 4;
+      const uint32_t base = tmem + ((uint32_t)(wq * 32) << 16) + g * 256;
+      uint32_t acc = 0;
+      __syncwarp();
+      t0 = clock64();
+      for (int it = 0; it < groups; ++it) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(base + c * 32, v);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc ^= v[j];
+          if (do_st) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = v[j] + it;
+            ptx::tmem_st_32x32b_x16(base + 128 + c * 16, w);
+            ptx::tmem_st_32x32b_x16(base + 192 + c * 16, w);
+          }
+        }
+        if (do_st) ptx::tmem_wait_st();
+      }
+      t1 = clock64();
+      if (lane == 0) {
+        out[16 + warp * 2] = t1 - t0;
+        out[16 + warp * 2 + 1] = acc;
+      }
+    }
+  } else if (warp == 8 && do_mma && (flags & 128)) {
+    // warp-uniform issue: all lanes run the loop, one elected lane issues (operands stay in uniform registers)
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = ptx::make_idesc_f16(1u, 128, n_dim);
+    const uint64_t a_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem));
+    const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem) + 32 * 1024);
+    uint32_t phase[2] = {0u, 0u};
+    t0 = clock64();
+    for (int it = 0; it < groups; ++it) {
+      const uint32_t d = tm + (it & 1) * 256;
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 24; ++k) {
+          if (a_tmem)
+            ptx::umma_f16_ts(d, d + 128 + (k & 7) * 8, b_desc + 2 * (k & 3), idesc, k != 0);
+          else
+            ptx::umma_f16_ss(d, a_desc + 2 * (k & 3), b_desc + 2 * (k & 3), idesc, k != 0);
+        }
+        ptx::umma_commit(&tail->bar_mma[it & 1]);
+      }
+      __syncwarp();
+      if (it > 0) {
+        ptx::mbar_wait(&tail->bar_mma[(it - 1) & 1], phase[(it - 1) & 1]);
+        phase[(it - 1) & 1] ^= 1u;
+      }
+    }
+    ptx::mbar_wait(&tail->bar_mma[(groups - 1) & 1], phase[(groups - 1) & 1]);
+    t1 = clock64();
+    if (lane == 0) out[0] = t1 - t0;
+  } else if (warp == 8 && lane == 0 && do_mma) {
+    const uint32_t idesc = ptx::make_idesc_f16(1u, 128, n_dim);
+    const uint64_t a_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem));
+    const uint64_t b_desc = ptx::make_desc_k_sw128(ptx::smem_u32(smem) + 32 * 1024);
+    uint32_t phase[2] = {0u, 0u};
+    t0 = clock64();
+    for (int it = 0; it < groups; ++it) {
+      const uint32_t d0 = tmem + (it & 1) * 256;
+      for (int k = 0; k < mma_per_group; ++k) {
+        const uint32_t d = alt_d ? tmem + (k & 1) * 256 : d0;
+        const uint32_t acc = no_acc ? 0u : (uint32_t)(k > (alt_d ? 1 : 0));
+        if (a_tmem)
+          ptx::umma_f16_ts(d, d + 128 + (k & 7) * 8, b_desc + 2 * (k & 3), idesc, acc);
+        else
+          ptx::umma_f16_ss(d, a_desc + 2 * (k & 3), b_desc + 2 * (k & 3), idesc, acc);
+      }
+      ptx::umma_commit(&tail->bar_mma[it & 1]);
+      if (it > 0) {  // keep one group queued behind the one executing
+        ptx::mbar_wait(&tail->bar_mma[(it - 1) & 1], phase[(it - 1) & 1]);
+        phase[(it - 1) & 1] ^= 1u;
+      }
+    }
+    ptx::mbar_wait(&tail->bar_mma[(groups - 1) & 1], phase[(groups - 1) & 1]);
+    t1 = clock64();
+    out[0] = t1 - t0;
+  }
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
+// MUFU.SIN throughput: `chains` independent values per thread, `iters` dependent steps each.
+template <int CHAINS>
+__global__ void mb_mufu(int iters, float seed, float* sink, unsigned long long* cyc) {
+  float x[CHAINS];
+#pragma unroll
+  for (int j = 0; j < CHAINS; ++j) x[j] = seed + 0.01f * (threadIdx.x + 37 * j);
+  __syncthreads();
+  const unsigned long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < CHAINS; ++j) x[j] = ptx::sin_approx(x[j]);
+  }
+  const unsigned long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < CHAINS; ++j) s += x[j];
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+#define CK(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e = (x);                                                           \
+    if (e != cudaSuccess) {                                                        \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); \
+      exit(1);                                                                     \
+    }                                                                              \
+  } while (0)
+
+int main() {
+  unsigned long long* d_out;
+  CK(cudaMalloc(&d_out, 64 * sizeof(unsigned long long)));
+  const size_t smem = 64 * 1024 + 1024 + sizeof(Tail);
+  CK(cudaFuncSetAttribute(mb_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  std::vector<unsigned long long> h(64);
+  struct Cfg { const char* name; int flags; int n; };
+  const Cfg cfgs[] = {
+      {"MMA SS  N=128 alone", 1, 128},       {"MMA TS  N=128 alone", 3, 128},
+      {"MMA SS  N=256 alone", 1, 256},       {"MMA TS  N=256 alone", 3, 256},
+      {"LDTM 4 warps alone", 4, 128},        {"LDTM+STTM 4 warps alone", 12, 128},
+      {"LDTM 8 warps alone", 20, 128},       {"LDTM+STTM 8 warps alone", 28, 128},
+      {"MMA SS N=128 + LDTM 4w", 5, 128},    {"MMA TS N=128 + LDTM 4w", 7, 128},
+      {"MMA SS N=128 + LDTM+STTM 4w", 13, 128}, {"MMA TS N=128 + LDTM+STTM 4w", 15, 128},
+      {"MMA TS N=128 + LDTM+STTM 8w", 31, 128},
+      {"MMA SS N=128 uniform issue", 1 | 128, 128}, {"MMA TS N=128 uniform issue", 3 | 128, 128},
+      {"MMA TS N=128 uniform + LDTM+STTM 8w", 31 | 128, 128}, {"MMA SS N=128 uniform + LDTM+STTM 8w", 29 | 128, 128},
+      {"MMA TS N=256 uniform issue", 3 | 128, 256}, {"MMA SS N=256 uniform issue", 1 | 128, 256},
+      {"MMA TS N=64 uniform issue", 3 | 128, 64}, {"MMA SS N=64 uniform issue", 1 | 128, 64},
+      {"MMA TS N=32 uniform issue", 3 | 128, 32}, {"MMA TS N=192 uniform issue", 3 | 128, 192},
+      {"MMA SS N=128 alternate D", 1 | 32, 128}, {"MMA TS N=128 alternate D", 3 | 32, 128},
+      {"MMA SS N=128 no accumulate", 1 | 64, 128}, {"MMA TS N=128 no accumulate", 3 | 64, 128},
+      {"MMA SS N=64", 1, 64}, {"MMA TS N=64", 3, 64}, {"MMA SS N=32", 1, 32}, {"MMA SS N=16", 1, 16},
+      {"MMA SS N=192", 1, 192}, {"MMA TS N=64 alternate D", 3 | 32, 64},
+  };
+  const int groups = 64, per_group = 24;
+  for (const Cfg& c : cfgs) {
+    CK(cudaMemset(d_out, 0, 64 * sizeof(unsigned long long)));
+    mb_tensor<<<1, 320, smem>>>(c.flags, groups, per_group, c.n, d_out);
+    CK(cudaDeviceSynchronize());
+    mb_tensor<<<148, 320, smem>>>(c.flags, groups, per_group, c.n, d_out);  // whole chip, CTA 0..147 overwrite the same slots
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.data(), d_out, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    printf("%-32s", c.name);
+    if (c.flags & 1) printf(" mma: %7.1f clk/MMA (%llu clk / %d)", (double)h[0] / (groups * per_group), h[0], groups * per_group);
+    if (c.flags & 4) {
+      const double clk = (double)h[16];
+      const double bytes = (double)groups * 4 * 4096;  // per warp: 4 x LDTM.x32 of 4 KiB per group
+      printf("  ldtm warp0: %7.1f clk/LDTM.x32 (%.1f B/clk/warp, x%d warps)", clk / (groups * 4), bytes / clk,
+             (c.flags & 16) ? 8 : 4);
+    }
+    printf("\n");
+  }
+  // MUFU
+  float* d_sink;
+  CK(cudaMalloc(&d_sink, 148 * 1024 * sizeof(float)));
+  for (int warps : {4, 8, 16, 32}) {
+    const int iters = 2000;
+    mb_mufu<8><<<148, warps * 32>>>(iters, 0.3f, d_sink, d_out);
+    CK(cudaDeviceSynchronize());
+    mb_mufu<8><<<148, warps * 32>>>(iters, 0.3f, d_sink, d_out);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.data(), d_out, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const double sins = (double)iters * 8 * warps * 32;
+    printf("MUFU.SIN %2d warps/SM, 8 chains: %8llu clk -> %.2f sin/clk/SM\n", warps, h[0], sins / (double)h[0]);
+  }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int iters = 20000;
+  mb_mufu<8><<<148 * 2, 512>>>(iters, 0.3f, d_sink, d_out);
+  CK(cudaEventRecord(e0));
+  mb_mufu<8><<<148 * 2, 512>>>(iters, 0.3f, d_sink, d_out);
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  printf("MUFU.SIN chip-wide: %.3f T sin/s (%.3f ms for %.3e sins)\n", (double)iters * 8 * 512 * 296 / (ms * 1e-3) / 1e12, ms,
+         (double)iters * 8 * 512 * 296);
+  return 0;
+}
