@@ -16,7 +16,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libconfild_cnf.so")
 SOURCES = ["cnf_cabi.cu"]
-HEADERS = ["layout.cuh", "pack.cuh", "ptx.cuh", "simt.cuh", "tc_kernels.cuh", os.path.join("..", "..", "include", "confild_cnf.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "confild_cnf.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

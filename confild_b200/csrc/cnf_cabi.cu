@@ -121,7 +121,7 @@ int launch_tc_forward(const cnf_dims& d, const uint8_t* packed, const float* coo
 template <int H, int PREC>
 int dispatch_tc_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs,
                         const float* shift, float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
-  const bool reduce = env_int("CNF_TC_REDUCE", 1) != 0;
+  const bool reduce = env_int("CNF_TC_REDUCE", 0) != 0;
   if (stash) {
     return reduce ? launch_tc_forward<H, PREC, true, true>(d, packed, coords, cfs, shift, out, stash, T, P, st)
                   : launch_tc_forward<H, PREC, true, false>(d, packed, coords, cfs, shift, out, stash, T, P, st);
@@ -178,7 +178,7 @@ int launch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* co
 template <int PREC>
 int dispatch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs,
                          const float* shift, float* out, int64_t T, int64_t P, cudaStream_t st) {
-  return env_int("CNF_TC_REDUCE", 1) != 0 ? launch_tc2_forward<PREC, true>(d, packed, coords, cfs, shift, out, T, P, st)
+  return env_int("CNF_TC_REDUCE", 0) != 0 ? launch_tc2_forward<PREC, true>(d, packed, coords, cfs, shift, out, T, P, st)
                                            : launch_tc2_forward<PREC, false>(d, packed, coords, cfs, shift, out, T, P, st);
 }
 

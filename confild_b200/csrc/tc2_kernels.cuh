@@ -40,7 +40,7 @@ __device__ __forceinline__ void trace_event(int role, int& n, unsigned long long
 
 constexpr int kTc2H = 128;
 constexpr int kTc2EpiWarps = 16;                       // 2 tile slots x 2 column halves x 4 lane quarters
-constexpr int kTc2Threads = (kTc2EpiWarps + 2) * 32;   // + MMA issuer warp + weight producer warp
+constexpr int kTc2Threads = (kTc2EpiWarps + 3) * 32;   // + one MMA issuer warp per tile slot + weight producer warp
 constexpr int kTc2SlotCols = 256;
 
 struct Tc2SmemTail {
@@ -52,6 +52,7 @@ struct Tc2SmemTail {
   uint64_t b_empty[kTcMaxStages];
   uint64_t a_full[2];
   uint64_t d_full[2];
+  uint64_t turn[2];  // issue token passed between the two MMA issuer warps
   uint32_t tmem_base;
 };
 
@@ -77,6 +78,83 @@ __device__ __forceinline__ void tc2_store_a(uint32_t tmem_a, int c0, const float
   if (kSplit) ptx::tmem_st_32x32b_x16(tmem_a + 64 + c0 / 2, lo);
 }
 
+// 16 activations (columns c0..c0+15 of this thread's row) -> 8 packed words per part -> tcgen05.st.x8
+template <int PREC>
+__device__ __forceinline__ void tc2_store_a16(uint32_t tmem_a, int c0, const float (&h)[16]) {
+  constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float x0 = h[2 * e], x1 = h[2 * e + 1];
+    if (kSplit) {
+      hi[e] = ptx::pack_bf16x2_pinned(x0, x1);
+      lo[e] = ptx::pack_bf16x2_pinned(x0 - ptx::bf16lo_to_f32(hi[e]), x1 - ptx::bf16hi_to_f32(hi[e]));
+    } else {
+      hi[e] = ptx::pack_f16x2_pinned(x0, x1);
+    }
+  }
+  ptx::tmem_st_32x32b_x8(tmem_a + c0 / 2, hi);
+  if (kSplit) ptx::tmem_st_32x32b_x8(tmem_a + 64 + c0 / 2, lo);
+}
+
+template <bool REDUCE>
+__device__ __forceinline__ void tc2_sines16(const uint32_t (&v)[16], const float* __restrict__ sbuf, float (&h)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 s4 = *reinterpret_cast<const float4*>(sbuf + q * 4);
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float z = __uint_as_float(v[q * 4 + e]) + sv[e];
+      h[q * 4 + e] = ptx::sin_approx_pinned(REDUCE ? ptx::reduce_2pi(z) : z);
+    }
+  }
+}
+
+// One hidden layer for this thread's row and its warpgroup's 64 columns.
+// Software pipeline over four 16-column groups: the TMEM load of group c+2 and the sines (MUFU) of group c+1 are issued
+// before the bf16 split / pack (ALU) of group c, so the XU and ALU pipes overlap inside the warp.
+template <int PREC, bool REDUCE, bool LAST>
+__device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tmem_a, int col0,
+                                                 const float* __restrict__ sbuf, const float* __restrict__ w_out_s,
+                                                 int cout, float (&y)[4]) {
+  uint32_t v[2][16];
+  float hcur[16], hnext[16];
+  ptx::tmem_ld_32x32b_x16(lane_base + col0, v[0]);
+  ptx::tmem_wait_ld();
+  ptx::tmem_ld_32x32b_x16(lane_base + col0 + 16, v[1]);
+  tc2_sines16<REDUCE>(v[0], sbuf + col0, hnext);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int c0 = col0 + c * 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) hcur[j] = hnext[j];
+    if (c + 1 < 4) {
+      ptx::tmem_wait_ld();
+      tc2_sines16<REDUCE>(v[(c + 1) & 1], sbuf + c0 + 16, hnext);
+      if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(lane_base + c0 + 32, v[c & 1]);
+    }
+    if (!LAST) {
+      tc2_store_a16<PREC>(tmem_a, c0, hcur);
+    } else {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        if (o >= cout) continue;
+        float acc = y[o];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = *reinterpret_cast<const float4*>(w_out_s + o * kTc2H + c0 + q * 4);
+          acc = fmaf(w4.x, hcur[q * 4 + 0], acc);
+          acc = fmaf(w4.y, hcur[q * 4 + 1], acc);
+          acc = fmaf(w4.z, hcur[q * 4 + 2], acc);
+          acc = fmaf(w4.w, hcur[q * 4 + 3], acc);
+        }
+        y[o] = acc;
+      }
+    }
+  }
+}
+
 template <int PREC, bool REDUCE>
 __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
                                                                      const float* __restrict__ coords,
@@ -89,7 +167,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
   constexpr int kParts = kSplit ? 2 : 1;
   constexpr int kSPL = (H / kSlabK) * kParts;  // stages per layer: 4 (split) or 2
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, H);
-  constexpr int kMmaWarp = kTc2EpiWarps;  // the warp after it is the weight producer
+  constexpr int kMmaWarp = kTc2EpiWarps;  // warps kMmaWarp, kMmaWarp+1: MMA issuers of slot 0, 1; then the producer
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -106,11 +184,12 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
   if (threadIdx.x == 0) {
     for (int s = 0; s < num_stages; ++s) {
       ptx::mbar_init(&tail->b_full[s], 1);
-      ptx::mbar_init(&tail->b_empty[s], 1);
+      ptx::mbar_init(&tail->b_empty[s], 2);  // released by the commits of both slots' issuers
     }
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(&tail->a_full[g], 256);
       ptx::mbar_init(&tail->d_full[g], 1);
+      ptx::mbar_init(&tail->turn[g], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -142,8 +221,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
     const uint32_t bar_slot = 5 + g;         // named barrier of the slot's two warpgroups (256 threads)
     uint32_t d_phase = 0;
     CNF_TRACE_DECL;
-    const bool tracer = (wq == 0 && lane == 0);
-    [[maybe_unused]] const int trole = hf == 0 ? g : 4 + g;
+    const bool tracer = (lane == 0);
+    [[maybe_unused]] const int trole = 4 + warp;
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + g;
       if (tile >= tiles) continue;
@@ -182,8 +261,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       if (tracer) CNF_TRACE_EVENT(trole, 101);  // layer 0 done, a_full arrived
 
       float y[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int l = 1; l <= nl; ++l) {
+      // every hidden layer: wait for the layer's accumulator, activate, (re)write the A operand or run the head
+      auto layer_prologue = [&](int l) -> const float* {
         float* sbuf = tail->shift_s[g][l & 1];
         if (wq < 2) sbuf[col0 + row] = __ldg(sh + (size_t)l * H + col0 + row);
         ptx::bar_sync(bar_wg, 128);
@@ -194,49 +273,21 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         ptx::bar_sync(bar_slot, 256);
         ptx::tc_fence_after();
         if (tracer) CNF_TRACE_EVENT(trole, 300 + l);  // d_full observed
-        const bool last = (l == nl);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int c0 = col0 + c * 32;
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(lane_base + c0, v);
-          ptx::tmem_wait_ld();
-          float h[32];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 s4 = *reinterpret_cast<const float4*>(sbuf + c0 + q * 4);
-            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float z = __uint_as_float(v[q * 4 + e]) + sv[e];
-              h[q * 4 + e] = ptx::sin_approx(REDUCE ? ptx::reduce_2pi(z) : z);
-            }
-          }
-          if (!last) {
-            tc2_store_a<PREC>(tmem_a, c0, h);
-          } else {
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              if (o >= cout) continue;
-              float acc = y[o];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 w4 = *reinterpret_cast<const float4*>(tail->w_out_s + o * H + c0 + q * 4);
-                acc = fmaf(w4.x, h[q * 4 + 0], acc);
-                acc = fmaf(w4.y, h[q * 4 + 1], acc);
-                acc = fmaf(w4.z, h[q * 4 + 2], acc);
-                acc = fmaf(w4.w, h[q * 4 + 3], acc);
-              }
-              y[o] = acc;
-            }
-          }
-        }
-        if (!last) {
-          ptx::tmem_wait_st();
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&tail->a_full[g]);
-        }
+        return sbuf;
+      };
+#pragma unroll 1
+      for (int l = 1; l < nl; ++l) {
+        const float* sbuf = layer_prologue(l);
+        tc2_hidden_layer<PREC, REDUCE, false>(lane_base, tmem_a, col0, sbuf, tail->w_out_s, cout, y);
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tail->a_full[g]);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
+      }
+      {
+        const float* sbuf = layer_prologue(nl);
+        tc2_hidden_layer<PREC, REDUCE, true>(lane_base, tmem_a, col0, sbuf, tail->w_out_s, cout, y);
+        if (tracer) CNF_TRACE_EVENT(trole, 400 + nl);
       }
       // ---- head: combine the two column halves, 12-byte store per point
       ptx::tc_fence_before();
@@ -252,62 +303,74 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       }
     }
     ptx::tc_fence_before();
-  } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
-    // The whole warp walks the (uniform) schedule and polls the barriers; one elected lane issues.  Keeping the
-    // control flow converged keeps every tcgen05 operand in uniform registers: the issue loop must sustain one
-    // UTCHMMA per ~64-85 clk, which a divergent single-lane loop (R2UR moves + waterfall loop per MMA) cannot.
+  } else if (warp < kMmaWarp + 2) {
+    // ===================== MMA issuers (one warp per tile slot) =====================
+    // Each warp walks the (uniform) schedule of its slot and polls the barriers; one elected lane issues.  Keeping
+    // the control flow converged keeps every tcgen05 operand in uniform registers: a divergent single-lane loop
+    // (R2UR moves + a waterfall loop per MMA) cannot sustain one UTCHMMA per ~85 clk.  Two issuers keep the tensor
+    // pipe's queue fed back to back: while one waits for its slot's A operand the other is issuing.
+    const int g = warp - kMmaWarp;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t ring_addr = ptx::smem_u32(ring);
-    uint32_t a_phase0 = 0u, a_phase1 = 0u;
-    int slot0 = 0;         // ring slot of stage 0 of the current layer
-    uint32_t phase0 = 0;   // its mbarrier parity
+    const uint32_t tmem_d = tmem_u + g * kTc2SlotCols;
+    const uint32_t tmem_a = tmem_d + 128;
+    uint32_t a_phase = 0u;
+    uint32_t turn_phase = g == 0 ? 1u : 0u;  // slot 0 issues first (a fresh barrier passes a parity-1 wait)
+    int slot0 = 0;       // ring slot of stage 0 of the current layer
+    uint32_t ph0 = 0;    // its mbarrier parity
     CNF_TRACE_DECL;
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-      const int nvalid = (2 * pair + 1 < tiles) ? 2 : 1;
+      const bool mine = (2 * pair + g < tiles);  // an odd tile count leaves slot 1 idle in the last pair
       for (int l = 1; l <= nl; ++l) {
+        // 1. everything this layer needs, waited for BEFORE taking the issue token
+        if (mine) {
+          int slot = slot0;
+          uint32_t ph = ph0;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (g < nvalid) {
-            if (lane == 0) CNF_TRACE_EVENT(2, 1000 + g * 100 + l);  // start waiting a_full[g]
-            ptx::mbar_wait(&tail->a_full[g], g == 0 ? a_phase0 : a_phase1);
-            if (g == 0) a_phase0 ^= 1u; else a_phase1 ^= 1u;
-            ptx::tc_fence_after();
-            if (lane == 0) CNF_TRACE_EVENT(2, 2000 + g * 100 + l);  // a_full observed
-            const uint32_t tmem_d = tmem_u + g * kTc2SlotCols;
-            const uint32_t tmem_a = tmem_d + 128;
-            int slot = slot0;
-            uint32_t ph = phase0;
+          for (int s = 0; s < kSPL; ++s) {  // weights first: they landed long ago (the ring is three layers deep)
+            ptx::mbar_wait(&tail->b_full[slot], ph);
+            if (++slot == num_stages) { slot = 0; ph ^= 1u; }
+          }
+          if (lane == 0) CNF_TRACE_EVENT(2 + g, 1000 + l);  // start waiting a_full[g]
+          ptx::mbar_wait(&tail->a_full[g], a_phase);
+          a_phase ^= 1u;
+          if (lane == 0) CNF_TRACE_EVENT(2 + g, 2000 + l);  // operands ready
+        }
+        // 2. strict alternation slot 0, slot 1, slot 0, ... : the epilogue of one slot overlaps the MMAs of the other
+        ptx::mbar_wait(&tail->turn[g], turn_phase);
+        turn_phase ^= 1u;
+        ptx::tc_fence_after();
+        // 3. the layer's MMAs back to back (24 for the bf16 split, 8 for fp16), then hand the token over
+        if (ptx::elect_one()) {
+          int slot = slot0;
 #pragma unroll
-            for (int s = 0; s < kSPL; ++s) {
-              if (g == 0) {  // first use of the stage: its bytes must have landed
-                ptx::mbar_wait(&tail->b_full[slot], ph);
-                ptx::tc_fence_after();
-              }
+          for (int s = 0; s < kSPL; ++s) {
+            if (mine) {
               const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
               const int ks = s / kParts, part = s % kParts;
-              if (ptx::elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const uint32_t a_hi = tmem_a + (ks * 4 + kk) * 8;  // 16 K elements = 8 packed columns
-                  if (part == 0) {
-                    ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (ks | kk) != 0);
-                    if (kSplit) ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
-                  } else {
-                    ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
-                  }
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t a_hi = tmem_a + (ks * 4 + kk) * 8;  // 16 K elements = 8 packed columns
+                if (part == 0) {
+                  ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (ks | kk) != 0);
+                  if (kSplit) ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
+                } else {
+                  ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
                 }
-                if (g == nvalid - 1) ptx::umma_commit(&tail->b_empty[slot]);  // last reader frees the stage
-                if (s == kSPL - 1) ptx::umma_commit(&tail->d_full[g]);
               }
-              __syncwarp();
-              if (++slot == num_stages) { slot = 0; ph ^= 1u; }
+              ptx::umma_commit(&tail->b_empty[slot]);
+            } else {
+              ptx::mbar_arrive(&tail->b_empty[slot]);  // idle slot: still release its share of the stage
             }
-            if (lane == 0) CNF_TRACE_EVENT(2, 3000 + g * 100 + l);  // all MMAs of (g,l) issued + committed
+            if (++slot == num_stages) slot = 0;
           }
+          if (mine) ptx::umma_commit(&tail->d_full[g]);
+          ptx::mbar_arrive(&tail->turn[g ^ 1]);
         }
+        __syncwarp();
+        if (mine && lane == 0) CNF_TRACE_EVENT(2 + g, 3000 + l);  // all MMAs of (g,l) issued + committed
         slot0 += kSPL;
-        if (slot0 >= num_stages) { slot0 -= num_stages; phase0 ^= 1u; }
+        if (slot0 >= num_stages) { slot0 -= num_stages; ph0 ^= 1u; }
       }
     }
   } else {

@@ -52,7 +52,9 @@ __host__ __device__ constexpr size_t tc_smem_bytes(int num_stages) {
 }
 
 // ------------------------------------------------------------------ shared pieces
-// Issue all MMAs of one hidden layer (single thread).  `slot`/`phase` walk the weight ring.
+// Issue all MMAs of one hidden layer.  Called by the WHOLE (converged) MMA warp: every lane polls the barriers and one
+// elected lane issues, which keeps the tcgen05 operands in uniform registers (a divergent single-lane loop pays R2UR
+// moves and a waterfall loop per MMA and cannot keep the tensor pipe fed).  `slot`/`phase` walk the weight ring.
 template <int H, int PREC>
 __device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_addr, uint32_t tmem_d, TcSmemTail* tail,
                                                int num_stages, int& slot, uint32_t& phase) {
@@ -66,29 +68,34 @@ __device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_ad
       // weights, high part (or the only part): pairs with a_hi and a_lo
       ptx::mbar_wait(&tail->b_full[slot], phase);
       ptx::tc_fence_after();
-      {
+      if (ptx::elect_one()) {
         const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {  // 4 x K=16 inside the 128-byte row: +32 bytes = +2 in the address field
           ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, (ks | kk) != 0);
           if (C::kSplit) ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_lo + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
         }
+        ptx::umma_commit(&tail->b_empty[slot]);
       }
-      ptx::umma_commit(&tail->b_empty[slot]);
+      __syncwarp();
       if (++slot == num_stages) { slot = 0; phase ^= 1u; }
       if (C::kSplit) {  // weights, low part: pairs with a_hi only
         ptx::mbar_wait(&tail->b_full[slot], phase);
         ptx::tc_fence_after();
-        const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+        if (ptx::elect_one()) {
+          const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
-        ptx::umma_commit(&tail->b_empty[slot]);
+          for (int kk = 0; kk < 4; ++kk)
+            ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
+          ptx::umma_commit(&tail->b_empty[slot]);
+        }
+        __syncwarp();
         if (++slot == num_stages) { slot = 0; phase ^= 1u; }
       }
     }
   }
-  ptx::umma_commit(&tail->d_full);
+  if (ptx::elect_one()) ptx::umma_commit(&tail->d_full);
+  __syncwarp();
 }
 
 // Convert 32 activations (columns c0..c0+31 of this thread's row) to the 16-bit operand format and
@@ -272,9 +279,10 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
     }
     ptx::tc_fence_before();
   } else if (warp == 4) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    {
       const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int slot = 0;
       uint32_t b_phase = 0, a_phase = 0;
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
           ptx::mbar_wait(&tail->a_full, a_phase);
           a_phase ^= 1u;
           ptx::tc_fence_after();
-          tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_base, tail, num_stages, slot, b_phase);
+          tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
         }
       }
     }
@@ -454,8 +462,9 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_backward_ke
       }
     }
   } else if (warp == 4) {
-    if (lane == 0) {
+    {
       const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int slot = 0;
       uint32_t b_phase = 0, a_phase = 0;
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -463,7 +472,7 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_backward_ke
           ptx::mbar_wait(&tail->a_full, a_phase);
           a_phase ^= 1u;
           ptx::tc_fence_after();
-          tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_base, tail, num_stages, slot, b_phase);
+          tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
         }
       }
     }

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "ptx.cuh"
+#include "tc2_kernels.cuh"
 
 using namespace cnf;
 
@@ -155,6 +156,42 @@ __global__ void mb_mufu(int iters, float seed, float* sink, unsigned long long* 
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// Epilogue alone: `nwarps` warps each run the hidden-layer epilogue of the H=128 kernel back to back
+// (no MMA, no hand-shakes), to size E = epilogue time per layer as a function of warps per SM sub-partition.
+template <int PREC>
+__global__ void __launch_bounds__(576, 1) mb_epilogue(int iters, unsigned long long* out) {
+  __shared__ float sbuf[128];
+  __shared__ float wout[4 * 128];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) sbuf[i] = 0.001f * i;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) wout[i] = 0.01f;
+  if (warp == 0) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int g = (warp / 8) & 1, hf = (warp / 4) & 1, wq = warp % 4;
+  const uint32_t lane_base = tmem + ((uint32_t)(wq * 32) << 16) + g * 256;
+  float y[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+  const unsigned long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    tc2_hidden_layer<PREC, false, false>(lane_base, lane_base + 128, 64 * hf, sbuf, wout, 3, y);
+    ptx::tmem_wait_st();
+  }
+  const unsigned long long t1 = clock64();
+  if (lane == 0) out[warp] = t1 - t0;
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
 #define CK(x)                                                                      \
   do {                                                                             \
     cudaError_t e = (x);                                                           \
@@ -206,6 +243,20 @@ int main() {
              (c.flags & 16) ? 8 : 4);
     }
     printf("\n");
+  }
+  for (int warps : {4, 8, 16}) {
+    const int iters = 200;
+    CK(cudaMemset(d_out, 0, 64 * sizeof(unsigned long long)));
+    mb_epilogue<CNF_PREC_BF16X3><<<148, warps * 32>>>(iters, d_out);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.data(), d_out, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    printf("epilogue bf16x3 %2d warps/SM: warp0 %7.1f clk per 64-column layer epilogue (last warp %7.1f)\n", warps,
+           (double)h[0] / iters, (double)h[warps - 1] / iters);
+    mb_epilogue<CNF_PREC_FP16><<<148, warps * 32>>>(iters, d_out);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.data(), d_out, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    printf("epilogue fp16   %2d warps/SM: warp0 %7.1f clk per 64-column layer epilogue (last warp %7.1f)\n", warps,
+           (double)h[0] / iters, (double)h[warps - 1] / iters);
   }
   // MUFU
   float* d_sink;

@@ -14,26 +14,33 @@ m = cb.SIRENAutodecoder_film(2,128,3,10,128, precision=prec); m.load_state_dict(
 c, l = coords.cuda()[None], lat.cuda()[:, None]
 with torch.no_grad():
     m(c, l); torch.cuda.synchronize()
-    buf = torch.zeros(6 * 8192, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(20 * 8192, dtype=torch.int64, device="cuda")
     lib = _native.load()
     assert lib.cnf_debug_set_trace(ctypes.c_void_p(buf.data_ptr())) == 0
     m(c, l); torch.cuda.synchronize()
-b = buf.cpu().view(6, 4096, 2)
+b = buf.cpu().view(20, 4096, 2)
 t0 = int(b[b[:, :, 1] > 0][:, 1].min())
-for role, name in enumerate(["WG0", "WG1", "MMA", "PROD", "WG0hf1", "WG1hf1"]):
-    ev = [(int(c), int(t) - t0) for c, t in b[role] if t > 0]
-    # skip first tile (cold), print second tile-pair
-    print(name, "events", len(ev))
-    start = None
-    shown = 0
-    for i, (c, t) in enumerate(ev):
-        if role in (0, 1, 4, 5) and c == 100:
-            shown += 1
-        if role == 2 and c % 100 == 1 and 1000 <= c < 1100:
-            shown += 1
-        if role == 3 and c == 6010:
-            shown += 1
-        if shown == 3:
-            print(f"  {c:5d} t={t:8d}" + (f"  (+{t - ev[i-1][1]})" if i else ""))
-        if shown > 3:
-            break
+import collections
+ev = {}
+for role in range(20):
+    ev[role] = [(int(c), int(t) - t0) for c, t in b[role] if t > 0]
+# MMA thread = role 2; epilogue warps = role 4 + warp
+mma0, mma1 = ev[2], ev[3]
+def nth(evs, code, n):
+    k = 0
+    for c, t in evs:
+        if c == code:
+            if k == n: return t
+            k += 1
+    return None
+TILE = 3
+for l in (3, 4, 5):
+    print(f"--- tile-pair #{TILE}, layer {l}")
+    for g in (0, 1):
+        mma = mma0 if g == 0 else mma1
+        a_obs = nth(mma, 2000 + l, TILE); issued = nth(mma, 3000 + l, TILE)
+        a_obs_next = nth(mma, 2000 + l + 1, TILE)
+        print(f"  MMA slot {g}: a_full seen {a_obs}, issued+committed {issued} (+{issued - a_obs}); next a_full seen {a_obs_next}")
+        for w in range(8 * g, 8 * g + 8):
+            d = nth(ev[4 + w], 300 + l, TILE); e = nth(ev[4 + w], 400 + l, TILE)
+            print(f"    warp {w:2d} (hf={(w // 4) % 2} wq={w % 4}): d_full seen {d} (+{d - issued}), epilogue done {e} (E={e - d})")
