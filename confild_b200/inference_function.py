@@ -14,8 +14,9 @@ from typing import Optional
 
 import torch
 
-#: upper bound of decoded output bytes per kernel launch (frames per chunk follow from it)
-CHUNK_OUTPUT_BYTES = 1 << 30
+#: upper bound of decoded output bytes per kernel launch (frames per chunk follow from it); small enough that the
+#: device->host copy of one chunk overlaps the decode of the next, large enough to fill the GPU (>= 148 tile pairs)
+CHUNK_OUTPUT_BYTES = 128 << 20
 
 
 def _frames_per_chunk(t_size: int, m_size: int, cout: int, batch_size: int) -> int:

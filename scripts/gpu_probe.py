@@ -66,6 +66,36 @@ def timeit(case, T, P, prec, iters=5):
     print(f"time {case} T={T} P={P} {prec}: {ms:.3f} ms  -> {T * P / ms / 1e6:.3f} G pf/s  launch={_native.query_launch(m._cdims(), m._precision_code(), T, P)}", flush=True)
 
 
+def time_dps(case, T, P, prec, iters=5):
+    dims = O.CASE_SHAPES[case]
+    sd = O.init_params(*dims, seed=0)
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    m = model(dims, sd, prec)
+    c = coords.cuda()[None]
+    mask = torch.zeros(P, 1, device="cuda")
+    mask[torch.randperm(P, device="cuda")[:1000]] = 1.0
+    y_meas = torch.randn(T, P, dims[2], device="cuda") * 0.05
+
+    def step():
+        l = lat.cuda()[:, None].requires_grad_(True)
+        y = m(c, l)
+        loss = torch.linalg.norm((y_meas - y) * mask)
+        (g,) = torch.autograd.grad(loss, l)
+        return g
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"time DPS fwd+bwd {case} T={T} P={P} {prec}: {ms:.3f} ms -> {T * P / ms / 1e6:.3f} G pf/s", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0), flush=True)
@@ -84,3 +114,10 @@ if __name__ == "__main__":
         for prec in ("bf16x3", "fp16"):
             timeit("case4", 16, 16384, prec)
         timeit("case1", 16, 16384, "fp32", iters=2)
+    if what in ("all", "dps"):
+        for prec in ("bf16x3", "fp16", "fp32"):
+            time_dps("case1", 64, 16384, prec)
+        for prec in ("bf16x3", "fp16"):
+            time_dps("case4", 64, 16384, prec)
+        time_dps("case4", 384, 10, "bf16x3")
+        time_dps("case4", 384, 1000, "bf16x3")
