@@ -204,6 +204,7 @@ def main_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (no NCCL version banner)
         dist.init_process_group("nccl", device_id=dev)
 
     cin, L, cout, nl, H = DIMS

@@ -142,7 +142,7 @@ int dispatch_tc_forward_h(const cnf_dims& d, const uint8_t* packed, const float*
 }
 
 // H = 128 fast path (activations in TMEM, two tiles in flight, one CTA per SM).
-bool use_tc2(const cnf_dims& d, bool stash) { return d.H == cnf::kTc2H && !stash && env_int("CNF_TC2", 1) != 0; }
+bool use_tc2(const cnf_dims& d) { return d.H == cnf::kTc2H && env_int("CNF_TC2", 1) != 0; }
 
 int make_tc2_plan(const DeviceInfo& di, int64_t tiles, TcPlan* plan) {
   const size_t fixed = cnf::tc2_smem_bytes(0);
@@ -160,26 +160,46 @@ int make_tc2_plan(const DeviceInfo& di, int64_t tiles, TcPlan* plan) {
   return CNF_OK;
 }
 
-template <int PREC, bool REDUCE>
+template <int PREC, bool REDUCE, bool STASH>
 int launch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs, const float* shift,
-                       float* out, int64_t T, int64_t P, cudaStream_t st) {
+                       float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
   TcPlan plan;
   if (int rc = make_tc2_plan(di, tiles, &plan)) return rc;
-  auto kern = cnf::tc2_forward_kernel<PREC, REDUCE>;
+  auto kern = cnf::tc2_forward_kernel<PREC, REDUCE, STASH>;
   CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-  kern<<<(unsigned)plan.grid, cnf::kTc2Threads, plan.smem, st>>>(d, packed, coords, cfs, shift, out, T, P, plan.stages);
+  kern<<<(unsigned)plan.grid, cnf::kTc2Threads, plan.smem, st>>>(d, packed, coords, cfs, shift, out,
+                                                                 reinterpret_cast<__half*>(stash), T, P, plan.stages);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;
 }
 
 template <int PREC>
 int dispatch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs,
-                         const float* shift, float* out, int64_t T, int64_t P, cudaStream_t st) {
-  return env_int("CNF_TC_REDUCE", 0) != 0 ? launch_tc2_forward<PREC, true>(d, packed, coords, cfs, shift, out, T, P, st)
-                                           : launch_tc2_forward<PREC, false>(d, packed, coords, cfs, shift, out, T, P, st);
+                         const float* shift, float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
+  const bool reduce = env_int("CNF_TC_REDUCE", 0) != 0;
+  if (stash)
+    return reduce ? launch_tc2_forward<PREC, true, true>(d, packed, coords, cfs, shift, out, stash, T, P, st)
+                  : launch_tc2_forward<PREC, false, true>(d, packed, coords, cfs, shift, out, stash, T, P, st);
+  return reduce ? launch_tc2_forward<PREC, true, false>(d, packed, coords, cfs, shift, out, stash, T, P, st)
+                : launch_tc2_forward<PREC, false, false>(d, packed, coords, cfs, shift, out, stash, T, P, st);
+}
+
+int launch_tc2_backward(const cnf_dims& d, const uint8_t* packed, const float* gout, const void* stash, float* gshift,
+                        int64_t T, int64_t P, cudaStream_t st) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
+  TcPlan plan;
+  if (int rc = make_tc2_plan(di, tiles, &plan)) return rc;
+  auto kern = cnf::tc2_backward_kernel;
+  CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  kern<<<(unsigned)plan.grid, cnf::kTc2Threads, plan.smem, st>>>(d, packed, gout, reinterpret_cast<const __half*>(stash),
+                                                                 gshift, T, P, plan.stages);
+  CNF_CUDA(cudaGetLastError());
+  return CNF_OK;
 }
 
 template <int H>
@@ -344,10 +364,12 @@ int cnf_forward(const cnf_dims* dims, const void* d_packed, int precision, const
                 "tensor-core path needs H in {128,256,384}, nl>=1, cin<=4, cout<=4 (got H=%d nl=%d cin=%d cout=%d); "
                 "use CNF_PREC_FP32",
                 dims->H, dims->nl, dims->cin, dims->cout);
-  if (use_tc2(*dims, d_stash != nullptr)) {
+  if (use_tc2(*dims)) {
     return precision == CNF_PREC_BF16X3
-               ? dispatch_tc2_forward<CNF_PREC_BF16X3>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out, T, P, st)
-               : dispatch_tc2_forward<CNF_PREC_FP16>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out, T, P, st);
+               ? dispatch_tc2_forward<CNF_PREC_BF16X3>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out,
+                                                       d_stash, T, P, st)
+               : dispatch_tc2_forward<CNF_PREC_FP16>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out,
+                                                     d_stash, T, P, st);
   }
   if (precision == CNF_PREC_BF16X3)
     return dispatch_tc_forward_h<CNF_PREC_BF16X3>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out, d_stash,
@@ -384,6 +406,7 @@ int cnf_backward(const cnf_dims* dims, const void* d_packed, int precision, cons
   if (!tc_ok(*dims))
     return fail(CNF_ERR_UNSUPPORTED, "tensor-core path unsupported for H=%d nl=%d cin=%d cout=%d; use CNF_PREC_FP32",
                 dims->H, dims->nl, dims->cin, dims->cout);
+  if (use_tc2(*dims)) return launch_tc2_backward(*dims, packed, d_gout, d_stash, d_gshift, T, P, st);
   switch (dims->H) {
     case 128: return launch_tc_backward<128>(*dims, packed, d_gout, d_stash, d_gshift, T, P, st);
     case 256: return launch_tc_backward<256>(*dims, packed, d_gout, d_stash, d_gshift, T, P, st);
@@ -412,7 +435,7 @@ int cnf_query_launch(const cnf_dims* dims, int precision, int64_t T, int64_t P, 
     TcPlan plan;
     int rc = CNF_ERR_UNSUPPORTED;
     const bool x3 = precision == CNF_PREC_BF16X3;
-    if (use_tc2(*dims, false)) {
+    if (use_tc2(*dims)) {
       if (int rc2 = make_tc2_plan(di, tiles, &plan)) return rc2;
       const int64_t v2[7] = {di.sms, plan.grid, cnf::kTc2Threads, (int64_t)plan.smem, 1, 512, 2 * cnf::kTileM};
       for (int i = 0; i < n && i < 7; ++i) values[i] = v2[i];

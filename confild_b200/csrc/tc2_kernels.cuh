@@ -97,8 +97,23 @@ __device__ __forceinline__ void tc2_store_a16(uint32_t tmem_a, int c0, const flo
   if (kSplit) ptx::tmem_st_32x32b_x8(tmem_a + 64 + c0 / 2, lo);
 }
 
-template <bool REDUCE>
-__device__ __forceinline__ void tc2_sines16(const uint32_t (&v)[16], const float* __restrict__ sbuf, float (&h)[16]) {
+// 16 fp16 cosines of this thread's row -> 32 contiguous bytes of the backward stash (nullptr: row out of range)
+__device__ __forceinline__ void tc2_stash16(__half* dst, const float (&c)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) w[e] = ptx::pack_f16x2(c[2 * e], c[2 * e + 1]);
+  if (dst != nullptr) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+  __syncwarp();  // rows past P skip the store: reconverge before the next warp-aligned tcgen05 instruction
+}
+
+template <bool REDUCE, bool STASH>
+__device__ __forceinline__ void tc2_sines16(const uint32_t (&v)[16], const float* __restrict__ sbuf, float (&h)[16],
+                                            __half* stash_dst) {
+  float cs[16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 s4 = *reinterpret_cast<const float4*>(sbuf + q * 4);
@@ -106,24 +121,27 @@ __device__ __forceinline__ void tc2_sines16(const uint32_t (&v)[16], const float
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float z = __uint_as_float(v[q * 4 + e]) + sv[e];
-      h[q * 4 + e] = ptx::sin_approx_pinned(REDUCE ? ptx::reduce_2pi(z) : z);
+      const float r = REDUCE ? ptx::reduce_2pi(z) : z;
+      h[q * 4 + e] = ptx::sin_approx_pinned(r);
+      if (STASH) cs[q * 4 + e] = ptx::cos_approx(r);
     }
   }
+  if (STASH) tc2_stash16(stash_dst, cs);
 }
 
 // One hidden layer for this thread's row and its warpgroup's 64 columns.
 // Software pipeline over four 16-column groups: the TMEM load of group c+2 and the sines (MUFU) of group c+1 are issued
 // before the bf16 split / pack (ALU) of group c, so the XU and ALU pipes overlap inside the warp.
-template <int PREC, bool REDUCE, bool LAST>
+template <int PREC, bool REDUCE, bool LAST, bool STASH>
 __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tmem_a, int col0,
                                                  const float* __restrict__ sbuf, const float* __restrict__ w_out_s,
-                                                 int cout, float (&y)[4]) {
+                                                 int cout, float (&y)[4], __half* stash_l) {
   uint32_t v[2][16];
   float hcur[16], hnext[16];
   ptx::tmem_ld_32x32b_x16(lane_base + col0, v[0]);
   ptx::tmem_wait_ld();
   ptx::tmem_ld_32x32b_x16(lane_base + col0 + 16, v[1]);
-  tc2_sines16<REDUCE>(v[0], sbuf + col0, hnext);
+  tc2_sines16<REDUCE, STASH>(v[0], sbuf + col0, hnext, (STASH && stash_l) ? stash_l + col0 : nullptr);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int c0 = col0 + c * 16;
@@ -131,7 +149,8 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
     for (int j = 0; j < 16; ++j) hcur[j] = hnext[j];
     if (c + 1 < 4) {
       ptx::tmem_wait_ld();
-      tc2_sines16<REDUCE>(v[(c + 1) & 1], sbuf + c0 + 16, hnext);
+      tc2_sines16<REDUCE, STASH>(v[(c + 1) & 1], sbuf + c0 + 16, hnext,
+                                 (STASH && stash_l) ? stash_l + c0 + 16 : nullptr);
       if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(lane_base + c0 + 32, v[c & 1]);
     }
     if (!LAST) {
@@ -155,13 +174,13 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
   }
 }
 
-template <int PREC, bool REDUCE>
+template <int PREC, bool REDUCE, bool STASH>
 __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
                                                                      const float* __restrict__ coords,
                                                                      int64_t coord_frame_stride,
                                                                      const float* __restrict__ shift,
-                                                                     float* __restrict__ out, int64_t T, int64_t P,
-                                                                     int num_stages) {
+                                                                     float* __restrict__ out, __half* __restrict__ stash,
+                                                                     int64_t T, int64_t P, int num_stages) {
   constexpr int H = kTc2H;
   constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
   constexpr int kParts = kSplit ? 2 : 1;
@@ -236,6 +255,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         for (int j = 0; j < 4; ++j)
           if (j < cin) x[j] = cp[j];
       }
+      __half* st_row = (STASH && valid) ? stash + (t * P + p) * SH : nullptr;  // cos stash of this (frame, point)
       if (tracer) CNF_TRACE_EVENT(trole, 100);  // tile start
       ptx::bar_sync(bar_wg, 128);           // everyone is done with the previous tile's shift buffers
       if (wq < 2) tail->shift_s[g][0][col0 + row] = __ldg(sh + col0 + row);
@@ -245,15 +265,27 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
 #pragma unroll 1
       for (int c0 = col0; c0 < col0 + 64; c0 += 32) {
         float h[32];
+        [[maybe_unused]] float cs0[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float z = tail->shift_s[g][0][c0 + j];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (i < cin) z = fmaf(tail->w_first_s[(c0 + j) * cin + i], x[i], z);
-          h[j] = ptx::sin_approx(ptx::reduce_2pi(z));
+          const float r = ptx::reduce_2pi(z);
+          h[j] = ptx::sin_approx(r);
+          if (STASH) cs0[j] = ptx::cos_approx(r);
         }
         tc2_store_a<PREC>(tmem_a, c0, h);
+        if (STASH) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            float c16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) c16[j] = cs0[q * 16 + j];
+            tc2_stash16(st_row ? st_row + c0 + q * 16 : nullptr, c16);  // every lane calls it (it ends in __syncwarp)
+          }
+        }
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -278,7 +310,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
 #pragma unroll 1
       for (int l = 1; l < nl; ++l) {
         const float* sbuf = layer_prologue(l);
-        tc2_hidden_layer<PREC, REDUCE, false>(lane_base, tmem_a, col0, sbuf, tail->w_out_s, cout, y);
+        tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, col0, sbuf, tail->w_out_s, cout, y,
+                                                     st_row ? st_row + (size_t)l * H : nullptr);
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tail->a_full[g]);
@@ -286,7 +319,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       }
       {
         const float* sbuf = layer_prologue(nl);
-        tc2_hidden_layer<PREC, REDUCE, true>(lane_base, tmem_a, col0, sbuf, tail->w_out_s, cout, y);
+        tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, col0, sbuf, tail->w_out_s, cout, y,
+                                                    st_row ? st_row + (size_t)nl * H : nullptr);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + nl);
       }
       // ---- head: combine the two column halves, 12-byte store per point
@@ -301,6 +335,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         for (int o = 0; o < 4; ++o)
           if (o < cout) op[o] = ys[o] + __ldg(b_out + o);
       }
+      __syncwarp();  // rows past P skipped the store: reconverge before the next tile's warp-aligned instructions
     }
     ptx::tc_fence_before();
   } else if (warp < kMmaWarp + 2) {
@@ -381,6 +416,259 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       uint32_t phase = 0;
       for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
         for (int l = 0; l < nl; ++l) {
+          const uint8_t* src = wsrc + (size_t)l * kSPL * kStageBytes;
+          for (int s = 0; s < kSPL; ++s) {
+            ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kStageBytes);
+            ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
+                          &tail->b_full[slot]);
+            if (++slot == num_stages) { slot = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ backward, H = 128
+// Same skeleton as tc2_forward_kernel with the transposed weight image: per tile slot the A operand in TMEM is
+// delta_l (bf16 hi/lo), the accumulator is delta_l * (w0 W_l), and the activation warpgroups multiply by the stashed
+// cos of the layer below, reduce the tile's 128 points per column with a 16-shuffle transpose-reduce per 16 columns
+// and add the column sums into gshift with one red.global per (warp, column).
+#ifdef CNF_TRACE
+#define CNF_CHECK(cond, what, a, b)                                                                             \
+  do {                                                                                                          \
+    if (!(cond)) {                                                                                              \
+      printf("CNF_CHECK %s failed: %lld %lld (block %d thread %d)\n", what, (long long)(a), (long long)(b),     \
+             (int)blockIdx.x, (int)threadIdx.x);                                                                \
+      __trap();                                                                                                 \
+    }                                                                                                           \
+  } while (0)
+#else
+#define CNF_CHECK(cond, what, a, b)
+#endif
+
+__device__ __forceinline__ void tc2_colsum16_to_global(float (&v)[16], int lane, float* dst) {
+  // 4 halving rounds: after them lane L holds column (L >> 1) & 15 summed over the 16 lanes with the same bit 0
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool upper = (lane & (off * 2)) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off * 2);
+      v[i] = (upper ? v[i + off] : v[i]) + recv;
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  if ((lane & 1) == 0) atomicAdd(dst + (lane >> 1), v[0]);
+}
+
+// `src` is always a readable row: rows past P read the frame's row 0 (their delta is exactly zero anyway, because
+// their dL/dy is zero and every row of the chain only depends on itself), so the warp never diverges here.
+__device__ __forceinline__ void tc2_load_cos16(const __half* src, float (&c)[16]) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint4 w = __ldg(s4 + q);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[e]));
+      c[q * 8 + 2 * e] = f.x;
+      c[q * 8 + 2 * e + 1] = f.y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
+                                                                      const float* __restrict__ gout,
+                                                                      const __half* __restrict__ stash,
+                                                                      float* __restrict__ gshift, int64_t T, int64_t P,
+                                                                      int num_stages) {
+  constexpr int H = kTc2H;
+  constexpr int PREC = CNF_PREC_BF16X3;
+  constexpr int kSPL = (H / kSlabK) * 2;
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(1u, kTileM, H);
+  constexpr int kMmaWarp = kTc2EpiWarps;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  Tc2SmemTail* tail = reinterpret_cast<Tc2SmemTail*>(ring + (size_t)num_stages * kStageBytes);
+
+  const PackedLayout lay = make_layout(d);
+  const int nl = d.nl, cout = d.cout;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t PB = (P + kTileM - 1) / kTileM;
+  const int64_t tiles = T * PB;
+  const int64_t pairs = (tiles + 1) / 2;
+  const int64_t SH = (int64_t)(nl + 1) * H;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      ptx::mbar_init(&tail->b_full[s], 1);
+      ptx::mbar_init(&tail->b_empty[s], 2);
+    }
+    for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(&tail->a_full[g], 256);
+      ptx::mbar_init(&tail->d_full[g], 1);
+      ptx::mbar_init(&tail->turn[g], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  {
+    const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
+    for (int i = threadIdx.x; i < cout * H; i += kTc2Threads) tail->w_out_s[i] = w_out[i];
+  }
+  if (warp == kMmaWarp) {
+    ptx::tmem_alloc(&tail->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp < kTc2EpiWarps) {
+    const int g = warp / 8, hf = (warp / 4) & 1, wq = warp % 4;
+    const int row = wq * 32 + lane;
+    const int col0 = 64 * hf;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + g * kTc2SlotCols;
+    const uint32_t tmem_a = lane_base + 128;
+    const uint32_t bar_slot = 5 + g;
+    uint32_t d_phase = 0;
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + g;
+      if (tile >= tiles) continue;
+      const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
+      const bool valid = p < P;
+      float* gs = gshift + t * SH;
+      const __half* st_row = stash + (t * P + (valid ? p : 0)) * SH;
+      float gy[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          if (o < cout) gy[o] = gout[(t * P + p) * cout + o];
+      }
+      // ---- seed: delta at the last sine layer, delta_nl = (gy . W_out) .* cos_nl
+#pragma unroll 1
+      for (int c0 = col0; c0 < col0 + 64; c0 += 16) {
+        float cs[16], dl[16];
+        tc2_load_cos16(st_row + (size_t)nl * H + c0, cs);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float gsum = 0.f;
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < cout) gsum = fmaf(gy[o], tail->w_out_s[o * H + c0 + j], gsum);
+          dl[j] = gsum * cs[j];
+        }
+        tc2_store_a16<PREC>(tmem_a, c0, dl);
+        tc2_colsum16_to_global(dl, lane, gs + (size_t)nl * H + c0);
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tail->a_full[g]);
+
+#pragma unroll 1
+      for (int l = nl; l >= 1; --l) {
+        if (hf == 0 && wq == 0) ptx::mbar_wait(&tail->d_full[g], d_phase);
+        d_phase ^= 1u;
+        ptx::bar_sync(bar_slot, 256);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = col0; c0 < col0 + 64; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(lane_base + c0, v);
+          float cs[16], dl[16];
+          tc2_load_cos16(st_row + (size_t)(l - 1) * H + c0, cs);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
+          if (l > 1) tc2_store_a16<PREC>(tmem_a, c0, dl);
+          tc2_colsum16_to_global(dl, lane, gs + (size_t)(l - 1) * H + c0);
+        }
+        ptx::tc_fence_before();
+        if (l > 1) {
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tail->a_full[g]);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  } else if (warp < kMmaWarp + 2) {
+    const int g = warp - kMmaWarp;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t ring_addr = ptx::smem_u32(ring);
+    const uint32_t tmem_d = tmem_u + g * kTc2SlotCols;
+    const uint32_t tmem_a = tmem_d + 128;
+    uint32_t a_phase = 0u;
+    uint32_t turn_phase = g == 0 ? 1u : 0u;
+    int slot0 = 0;
+    uint32_t ph0 = 0;
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      const bool mine = (2 * pair + g < tiles);
+      for (int l = nl; l >= 1; --l) {
+        if (mine) {
+          int slot = slot0;
+          uint32_t ph = ph0;
+#pragma unroll
+          for (int s = 0; s < kSPL; ++s) {
+            ptx::mbar_wait(&tail->b_full[slot], ph);
+            if (++slot == num_stages) { slot = 0; ph ^= 1u; }
+          }
+          ptx::mbar_wait(&tail->a_full[g], a_phase);
+          a_phase ^= 1u;
+        }
+        ptx::mbar_wait(&tail->turn[g], turn_phase);
+        turn_phase ^= 1u;
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          int slot = slot0;
+#pragma unroll
+          for (int s = 0; s < kSPL; ++s) {
+            if (mine) {
+              const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+              const int ks = s / 2, part = s % 2;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t a_hi = tmem_a + (ks * 4 + kk) * 8;
+                if (part == 0) {
+                  ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (ks | kk) != 0);
+                  ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
+                } else {
+                  ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
+                }
+              }
+              ptx::umma_commit(&tail->b_empty[slot]);
+            } else {
+              ptx::mbar_arrive(&tail->b_empty[slot]);
+            }
+            if (++slot == num_stages) slot = 0;
+          }
+          if (mine) ptx::umma_commit(&tail->d_full[g]);
+          ptx::mbar_arrive(&tail->turn[g ^ 1]);
+        }
+        __syncwarp();
+        slot0 += kSPL;
+        if (slot0 >= num_stages) { slot0 -= num_stages; ph0 ^= 1u; }
+      }
+    }
+  } else {
+    if (lane == 0) {
+      const uint8_t* wsrc = packed + lay.tc_bwd_x3;
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+        for (int l = nl - 1; l >= 0; --l) {
           const uint8_t* src = wsrc + (size_t)l * kSPL * kStageBytes;
           for (int s = 0; s < kSPL; ++s) {
             ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);

@@ -216,7 +216,10 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
           sin_cos_of<true>(z, STASH, h[j], cs[j]);
         }
         tc_store_a<H, PREC>(a_smem, row, c0, h);
-        if (STASH && valid) stash_store_f16(st_row + c0, cs);
+        if (STASH) {
+          if (valid) stash_store_f16(st_row + c0, cs);
+          __syncwarp();
+        }
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
@@ -262,7 +265,10 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
               y[o] = acc;
             }
           }
-          if (STASH && valid) stash_store_f16(st_row + (size_t)l * H + c0, cs);
+          if (STASH) {
+            if (valid) stash_store_f16(st_row + (size_t)l * H + c0, cs);
+            __syncwarp();
+          }
         }
         if (!last) {
           ptx::tc_fence_before();
@@ -276,6 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
         for (int o = 0; o < 4; ++o)
           if (o < cout) op[o] = y[o] + __ldg(b_out + o);
       }
+      __syncwarp();  // rows past P skipped the store: reconverge before the next tile's warp-aligned instructions
     }
     ptx::tc_fence_before();
   } else if (warp == 4) {
@@ -397,23 +404,20 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_backward_ke
           if (o < cout) gy[o] = gout[(t * P + p) * cout + o];
       }
 
+      // rows past P read the frame's row 0 (st_row is clamped): their delta is exactly zero because their dL/dy is,
+      // and the warp stays converged for the warp-aligned tcgen05 instructions that follow
       auto load_cos = [&](int l, int c0, float (&c)[32]) {
-        if (valid) {
-          const uint4* s4 = reinterpret_cast<const uint4*>(st_row + (size_t)l * H + c0);
+        const uint4* s4 = reinterpret_cast<const uint4*>(st_row + (size_t)l * H + c0);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 w = __ldg(s4 + q);
-            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        for (int q = 0; q < 4; ++q) {
+          const uint4 w = __ldg(s4 + q);
+          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[e]));
-              c[q * 8 + 2 * e] = f.x;
-              c[q * 8 + 2 * e + 1] = f.y;
-            }
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[e]));
+            c[q * 8 + 2 * e] = f.x;
+            c[q * 8 + 2 * e + 1] = f.y;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) c[j] = 0.f;
         }
       };
 
