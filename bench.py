@@ -32,6 +32,11 @@ DIMS = (2, 128, 3, 10, 128)  # cin, L, cout, nl, H (oracle order)
 FRAMES, POINTS = 1024, 65536
 METRIC = "cnf_decode_point_frames_per_s"
 UNIT = "point-frames/s"
+#: chip-wide sin.approx (MUFU.SIN) throughput measured on this pool's B200 with scripts/microbench.cu
+#: (profiles/r01_microbench_mma_ldtm_mufu.txt): 15.98 sin/clk/SM, 4.625 T sin/s at 1.965 GHz
+MUFU_PEAK_SIN_PER_S = 4.625e12
+#: DRAM bytes of one tc2_forward_kernel launch at the bench size from `ncu --set full` (profiles/): read + write
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 764907008  # 15.86 MB read + 749.05 MB written (profiles/r01_ncu_tc2_forward_case1_bf16x3_benchsize.txt)
 
 
 def flops_per_pf(cin, L, cout, nl, H):
@@ -186,6 +191,57 @@ class Affine11:
         return (y + 1) / 2 * (hi - lo) + lo
 
 
+def measure_extra(model, coords, lat, dev, args):
+    """Reported next to the headline (never folded into it): the single-pass fp16 fast mode on the same workload and
+    the DPS step of BASELINE config 4 (forward with stash + backward to the latents, 64 frames x 16,384 points)."""
+    import confild_b200 as cb
+    from oracle import cnf_oracle as O
+
+    cin, L, cout, nl, H = DIMS
+    T, P = args.frames, args.points
+    out = {}
+
+    def timed(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    if args.precision != "fp16":
+        fast = cb.SIRENAutodecoder_film(cin, L, cout, nl, H, precision="fp16")
+        fast.load_state_dict(model.state_dict())
+        fast = fast.eval().to(dev)
+        with torch.no_grad():
+            ms = timed(lambda: fast(coords, lat), 3)
+        out["fast_mode_fp16"] = {"value": T * P / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                                 "note": "single fp16 MMA per product; forward rel-L2 vs reference 3.8e-4 at case1 "
+                                         "(inside the 1e-3 contract, outside it for case3/case4)"}
+    Td, Pd = 64, 16384
+    cd, ld = O.synthetic_inputs(cin, L, Td, Pd)
+    cd, ld = cd.to(dev)[None], ld.to(dev)
+    mask = torch.zeros(Pd, 1, device=dev)
+    mask[torch.randperm(Pd, device=dev)[:1000]] = 1.0
+    y_meas = torch.randn(Td, Pd, cout, device=dev) * 0.05
+
+    def dps_step():
+        l = ld[:, None].detach().requires_grad_(True)
+        y = model(cd, l)
+        loss = torch.linalg.norm((y_meas - y) * mask)  # condition_methods.py:30-31
+        torch.autograd.grad(loss, l)                    # condition_methods.py:32
+
+    ms = timed(dps_step, 5)
+    out["dps_fwd_bwd"] = {"value": Td * Pd / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                          "workload": f"{CASE} shapes, {Td} latents x {Pd} points, 1000 random sensors, "
+                                      "forward(+cos stash) + loss + backward to dL/dlatent (BASELINE config 4)",
+                          "precision": args.precision}
+    return out
+
+
 def main_ours(args):
     import torch.distributed as dist
 
@@ -278,6 +334,10 @@ def main_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * T * P * e2e_steps / float(t.item())
 
+    extra = {}
+    if world == 1 and not args.no_extra:
+        extra = measure_extra(model, coords, lat, dev, args)
+
     if rank == 0:
         peaks, peak_src = load_peaks()
         kavg_ms = sum(kern_ms) / max(1, len(kern_ms))
@@ -285,7 +345,7 @@ def main_ours(args):
         ach_tf = fl / (kavg_ms * 1e-3) / 1e12
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
         sin_rate = sins_per_pf(*DIMS) * T * P / (kavg_ms * 1e-3)
-        mufu_peak = 16 * 148 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        mufu_peak = MUFU_PEAK_SIN_PER_S
         launch = _native.query_launch(model._cdims(), model._precision_code(), T, P)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -306,15 +366,18 @@ def main_ours(args):
                            "with pinned host buffers (mirror of cnf/inference_function.py:51-76)"},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                         "traffic": None, "kernel": "tc_forward_kernel" if args.precision != "fp32" else "simt_forward_kernel",
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                         "kernel": "tc2_forward_kernel" if args.precision != "fp32" else "simt_forward_kernel",
                          "kernel_ms": kavg_ms, "peak_source": f"{peak_src} bf16_tflops_sustained",
                          "algorithmic_flops_per_launch": fl,
-                         "mufu": {"achieved_gsin_s": sin_rate / 1e9, "nominal_peak_gsin_s": mufu_peak / 1e9,
+                         "mufu": {"achieved_gsin_s": sin_rate / 1e9, "measured_peak_gsin_s": mufu_peak / 1e9,
                                   "frac": sin_rate / mufu_peak}},
             "launch": dict(zip(("sms", "ctas", "threads", "smem_bytes", "ctas_per_sm", "tmem_cols", "tile_points"), launch)),
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -332,6 +395,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--points", type=int, default=POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the fast-mode and DPS side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)

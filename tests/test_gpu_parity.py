@@ -127,6 +127,26 @@ def test_dps_gradient_vs_oracle(case, T, P, sensors):
         assert err <= BWD_TOL[prec], (case, prec, err)
 
 
+@pytest.mark.parametrize("T,P", [(3, 300), (2, 129), (1, 300), (4, 129), (1, 1), (5, 257)])
+@pytest.mark.parametrize("case", ["case1", "case2"])
+def test_gradient_ragged_tiles(case, T, P):
+    """Odd tile counts (an idle second tile slot in the last pair) and rows past P inside a tile, with the backward
+    stash: the warp must stay converged around the warp-aligned tcgen05 instructions."""
+    dims = O.CASE_SHAPES[case]
+    sd = O.init_params(*dims, seed=0)
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    gout = torch.randn(T, P, dims[2], generator=torch.Generator().manual_seed(7))
+    want = O.forward(sd, coords[None], lat[:, None])
+    gwant = O.grad_latents_from_gout(sd, coords[None], lat[:, None], gout)
+    m = make_model(dims, sd, "bf16x3")
+    l = lat.cuda()[:, None].requires_grad_(True)
+    y = m(coords.cuda()[None], l)
+    (g,) = torch.autograd.grad(y, l, grad_outputs=gout.cuda())
+    torch.cuda.synchronize()
+    assert O.rel_l2(y, want) <= 1e-4
+    assert O.rel_l2(g, gwant) <= 1e-2
+
+
 def test_edge_shapes_and_batch_invariance():
     dims = O.CASE_SHAPES["case1"]
     sd = O.init_params(*dims, seed=0)
