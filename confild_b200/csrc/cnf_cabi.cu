@@ -76,29 +76,20 @@ struct TcPlan {
 template <int H, int PREC>
 int make_tc_plan(const DeviceInfo& di, int64_t tiles, TcPlan* plan) {
   using C = cnf::TcCfg<H, PREC>;
-  // Two resident CTAs per SM (one runs its MMAs while the other runs its sine epilogue) whenever the
-  // A operand leaves room for a >= 2-deep weight ring in half the shared memory; otherwise one CTA.
-  const size_t per_sm = (size_t)di.max_smem_optin + 1024;  // opt-in limit is per block; SM has 1 KiB more per block
-  int want = env_int("CNF_TC_CTAS_PER_SM", 0);
-  int best_ctas = 1, best_stages = 0;
-  for (int ctas = (want > 0 ? want : 2); ctas >= 1; --ctas) {
-    const size_t budget = per_sm / ctas - 1024;
-    const size_t fixed = cnf::tc_smem_bytes<H, PREC>(0);
-    if (budget <= fixed) continue;
-    int stages = (int)((budget - fixed) / cnf::kStageBytes);
-    if (stages > cnf::kTcMaxStages) stages = cnf::kTcMaxStages;
-    if ((int)C::kTmemCols * ctas > 512) continue;
-    if (stages >= 2) { best_ctas = ctas; best_stages = stages; break; }
-  }
-  if (best_stages < 2) return fail(CNF_ERR_UNSUPPORTED, "H=%d precision=%d does not fit in shared memory", H, PREC);
+  // One CTA per SM (16 activation warps + issuer + producer fill the register file); the weight ring takes whatever
+  // shared memory the A operand leaves: 2 stages at H=384 bf16x3, 6 at H=256 bf16x3, 12 otherwise.
+  const size_t fixed = cnf::tc_smem_bytes<H, PREC>(0);
+  if ((size_t)di.max_smem_optin <= fixed + 2 * cnf::kStageBytes)
+    return fail(CNF_ERR_UNSUPPORTED, "H=%d precision=%d does not fit in shared memory", H, PREC);
+  int stages = (int)(((size_t)di.max_smem_optin - fixed) / cnf::kStageBytes);
+  if (stages > cnf::kTcMaxStages) stages = cnf::kTcMaxStages;
   const int forced = env_int("CNF_TC_STAGES", 0);
-  if (forced >= 2 && forced <= best_stages) best_stages = forced;
-  plan->stages = best_stages;
-  plan->ctas_per_sm = best_ctas;
-  plan->smem = cnf::tc_smem_bytes<H, PREC>(best_stages);
+  if (forced >= 2 && forced <= stages) stages = forced;
+  plan->stages = stages;
+  plan->ctas_per_sm = 1;
+  plan->smem = cnf::tc_smem_bytes<H, PREC>(stages);
   plan->tmem_cols = C::kTmemCols;
-  const int64_t cap = (int64_t)di.sms * best_ctas;
-  plan->grid = tiles < cap ? tiles : cap;
+  plan->grid = tiles < di.sms ? tiles : di.sms;
   return CNF_OK;
 }
 

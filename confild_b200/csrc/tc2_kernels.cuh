@@ -17,26 +17,9 @@
 
 #include "layout.cuh"
 #include "ptx.cuh"
-#include "tc_kernels.cuh"
+#include "tc_common.cuh"
 
 namespace cnf {
-
-#ifdef CNF_TRACE
-// Debug build only: per-role event trace of CTA 0 (role r writes (code, clock64) pairs at trace[r*8192 + 2*n]).
-__device__ unsigned long long* g_trace = nullptr;
-__device__ __forceinline__ void trace_event(int role, int& n, unsigned long long code) {
-  if (g_trace != nullptr && blockIdx.x == 0 && n < 4000) {
-    g_trace[role * 8192 + 2 * n] = code;
-    g_trace[role * 8192 + 2 * n + 1] = clock64();
-    ++n;
-  }
-}
-#define CNF_TRACE_DECL int trace_n = 0
-#define CNF_TRACE_EVENT(role, code) trace_event(role, trace_n, code)
-#else
-#define CNF_TRACE_DECL
-#define CNF_TRACE_EVENT(role, code)
-#endif
 
 constexpr int kTc2H = 128;
 constexpr int kTc2EpiWarps = 16;                       // 2 tile slots x 2 column halves x 4 lane quarters
@@ -97,38 +80,6 @@ __device__ __forceinline__ void tc2_store_a16(uint32_t tmem_a, int c0, const flo
   if (kSplit) ptx::tmem_st_32x32b_x8(tmem_a + 64 + c0 / 2, lo);
 }
 
-// 16 fp16 cosines of this thread's row -> 32 contiguous bytes of the backward stash (nullptr: row out of range)
-__device__ __forceinline__ void tc2_stash16(__half* dst, const float (&c)[16]) {
-  uint32_t w[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) w[e] = ptx::pack_f16x2(c[2 * e], c[2 * e + 1]);
-  if (dst != nullptr) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
-  }
-  __syncwarp();  // rows past P skip the store: reconverge before the next warp-aligned tcgen05 instruction
-}
-
-template <bool REDUCE, bool STASH>
-__device__ __forceinline__ void tc2_sines16(const uint32_t (&v)[16], const float* __restrict__ sbuf, float (&h)[16],
-                                            __half* stash_dst) {
-  float cs[16];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 s4 = *reinterpret_cast<const float4*>(sbuf + q * 4);
-    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float z = __uint_as_float(v[q * 4 + e]) + sv[e];
-      const float r = REDUCE ? ptx::reduce_2pi(z) : z;
-      h[q * 4 + e] = ptx::sin_approx_pinned(r);
-      if (STASH) cs[q * 4 + e] = ptx::cos_approx(r);
-    }
-  }
-  if (STASH) tc2_stash16(stash_dst, cs);
-}
-
 // One hidden layer for this thread's row and its warpgroup's 64 columns.
 // Software pipeline over four 16-column groups: the TMEM load of group c+2 and the sines (MUFU) of group c+1 are issued
 // before the bf16 split / pack (ALU) of group c, so the XU and ALU pipes overlap inside the warp.
@@ -141,7 +92,7 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
   ptx::tmem_ld_32x32b_x16(lane_base + col0, v[0]);
   ptx::tmem_wait_ld();
   ptx::tmem_ld_32x32b_x16(lane_base + col0 + 16, v[1]);
-  tc2_sines16<REDUCE, STASH>(v[0], sbuf + col0, hnext, (STASH && stash_l) ? stash_l + col0 : nullptr);
+  tc_sines16<REDUCE, STASH>(v[0], sbuf + col0, hnext, (STASH && stash_l) ? stash_l + col0 : nullptr);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int c0 = col0 + c * 16;
@@ -149,7 +100,7 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
     for (int j = 0; j < 16; ++j) hcur[j] = hnext[j];
     if (c + 1 < 4) {
       ptx::tmem_wait_ld();
-      tc2_sines16<REDUCE, STASH>(v[(c + 1) & 1], sbuf + c0 + 16, hnext,
+      tc_sines16<REDUCE, STASH>(v[(c + 1) & 1], sbuf + c0 + 16, hnext,
                                  (STASH && stash_l) ? stash_l + c0 + 16 : nullptr);
       if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(lane_base + c0 + 32, v[c & 1]);
     }
@@ -283,7 +234,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
             float c16[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) c16[j] = cs0[q * 16 + j];
-            tc2_stash16(st_row ? st_row + c0 + q * 16 : nullptr, c16);  // every lane calls it (it ends in __syncwarp)
+            tc_stash16(st_row ? st_row + c0 + q * 16 : nullptr, c16);  // every lane calls it (it ends in __syncwarp)
           }
         }
       }
@@ -442,52 +393,6 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
 // delta_l (bf16 hi/lo), the accumulator is delta_l * (w0 W_l), and the activation warpgroups multiply by the stashed
 // cos of the layer below, reduce the tile's 128 points per column with a 16-shuffle transpose-reduce per 16 columns
 // and add the column sums into gshift with one red.global per (warp, column).
-#ifdef CNF_TRACE
-#define CNF_CHECK(cond, what, a, b)                                                                             \
-  do {                                                                                                          \
-    if (!(cond)) {                                                                                              \
-      printf("CNF_CHECK %s failed: %lld %lld (block %d thread %d)\n", what, (long long)(a), (long long)(b),     \
-             (int)blockIdx.x, (int)threadIdx.x);                                                                \
-      __trap();                                                                                                 \
-    }                                                                                                           \
-  } while (0)
-#else
-#define CNF_CHECK(cond, what, a, b)
-#endif
-
-__device__ __forceinline__ void tc2_colsum16_to_global(float (&v)[16], int lane, float* dst) {
-  // 4 halving rounds: after them lane L holds column (L >> 1) & 15 summed over the 16 lanes with the same bit 0
-#pragma unroll
-  for (int off = 8; off >= 1; off >>= 1) {
-    const bool upper = (lane & (off * 2)) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = upper ? v[i] : v[i + off];
-      const float recv = __shfl_xor_sync(0xffffffffu, send, off * 2);
-      v[i] = (upper ? v[i + off] : v[i]) + recv;
-    }
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-  if ((lane & 1) == 0) atomicAdd(dst + (lane >> 1), v[0]);
-}
-
-// `src` is always a readable row: rows past P read the frame's row 0 (their delta is exactly zero anyway, because
-// their dL/dy is zero and every row of the chain only depends on itself), so the warp never diverges here.
-__device__ __forceinline__ void tc2_load_cos16(const __half* src, float (&c)[16]) {
-  const uint4* s4 = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const uint4 w = __ldg(s4 + q);
-    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[e]));
-      c[q * 8 + 2 * e] = f.x;
-      c[q * 8 + 2 * e + 1] = f.y;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
                                                                       const float* __restrict__ gout,
                                                                       const __half* __restrict__ stash,
@@ -561,7 +466,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
 #pragma unroll 1
       for (int c0 = col0; c0 < col0 + 64; c0 += 16) {
         float cs[16], dl[16];
-        tc2_load_cos16(st_row + (size_t)nl * H + c0, cs);
+        tc_load_cos16(st_row + (size_t)nl * H + c0, cs);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float gsum = 0.f;
@@ -571,7 +476,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
           dl[j] = gsum * cs[j];
         }
         tc2_store_a16<PREC>(tmem_a, c0, dl);
-        tc2_colsum16_to_global(dl, lane, gs + (size_t)nl * H + c0);
+        tc_colsum16_to_global(dl, lane, gs + (size_t)nl * H + c0);
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -588,12 +493,12 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
           uint32_t v[16];
           ptx::tmem_ld_32x32b_x16(lane_base + c0, v);
           float cs[16], dl[16];
-          tc2_load_cos16(st_row + (size_t)(l - 1) * H + c0, cs);
+          tc_load_cos16(st_row + (size_t)(l - 1) * H + c0, cs);
           ptx::tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
           if (l > 1) tc2_store_a16<PREC>(tmem_a, c0, dl);
-          tc2_colsum16_to_global(dl, lane, gs + (size_t)(l - 1) * H + c0);
+          tc_colsum16_to_global(dl, lane, gs + (size_t)(l - 1) * H + c0);
         }
         ptx::tc_fence_before();
         if (l > 1) {

@@ -1,0 +1,109 @@
+// Pieces shared by the tensor-core kernels (tc_kernels.cuh: generic SS-mode, tc2_kernels.cuh: H = 128 TMEM-resident).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "layout.cuh"
+#include "ptx.cuh"
+
+namespace cnf {
+
+constexpr int kTcMaxStages = 12;
+
+#ifdef CNF_TRACE
+// Debug build only: per-role event trace of CTA 0 (role r writes (code, clock64) pairs at trace[r*8192 + 2*n]).
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_event(int role, int& n, unsigned long long code) {
+  if (g_trace != nullptr && blockIdx.x == 0 && n < 4000) {
+    g_trace[role * 8192 + 2 * n] = code;
+    g_trace[role * 8192 + 2 * n + 1] = clock64();
+    ++n;
+  }
+}
+#define CNF_TRACE_DECL int trace_n = 0
+#define CNF_TRACE_EVENT(role, code) trace_event(role, trace_n, code)
+#else
+#define CNF_TRACE_DECL
+#define CNF_TRACE_EVENT(role, code)
+#endif
+
+// 16 fp16 cosines of this thread's row -> 32 contiguous bytes of the backward stash (nullptr: row out of range)
+__device__ __forceinline__ void tc_stash16(__half* dst, const float (&c)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) w[e] = ptx::pack_f16x2(c[2 * e], c[2 * e + 1]);
+  if (dst != nullptr) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+  __syncwarp();  // rows past P skip the store: reconverge before the next warp-aligned tcgen05 instruction
+}
+
+template <bool REDUCE, bool STASH>
+__device__ __forceinline__ void tc_sines16(const uint32_t (&v)[16], const float* __restrict__ sbuf, float (&h)[16],
+                                            __half* stash_dst) {
+  float cs[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 s4 = *reinterpret_cast<const float4*>(sbuf + q * 4);
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float z = __uint_as_float(v[q * 4 + e]) + sv[e];
+      const float r = REDUCE ? ptx::reduce_2pi(z) : z;
+      h[q * 4 + e] = ptx::sin_approx_pinned(r);
+      if (STASH) cs[q * 4 + e] = ptx::cos_approx(r);
+    }
+  }
+  if (STASH) tc_stash16(stash_dst, cs);
+}
+
+#ifdef CNF_TRACE
+#define CNF_CHECK(cond, what, a, b)                                                                             \
+  do {                                                                                                          \
+    if (!(cond)) {                                                                                              \
+      printf("CNF_CHECK %s failed: %lld %lld (block %d thread %d)\n", what, (long long)(a), (long long)(b),     \
+             (int)blockIdx.x, (int)threadIdx.x);                                                                \
+      __trap();                                                                                                 \
+    }                                                                                                           \
+  } while (0)
+#else
+#define CNF_CHECK(cond, what, a, b)
+#endif
+
+__device__ __forceinline__ void tc_colsum16_to_global(float (&v)[16], int lane, float* dst) {
+  // 4 halving rounds: after them lane L holds column (L >> 1) & 15 summed over the 16 lanes with the same bit 0
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool upper = (lane & (off * 2)) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off * 2);
+      v[i] = (upper ? v[i + off] : v[i]) + recv;
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  if ((lane & 1) == 0) atomicAdd(dst + (lane >> 1), v[0]);
+}
+
+// `src` is always a readable row: rows past P read the frame's row 0 (their delta is exactly zero anyway, because
+// their dL/dy is zero and every row of the chain only depends on itself), so the warp never diverges here.
+__device__ __forceinline__ void tc_load_cos16(const __half* src, float (&c)[16]) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint4 w = __ldg(s4 + q);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[e]));
+      c[q * 8 + 2 * e] = f.x;
+      c[q * 8 + 2 * e + 1] = f.y;
+    }
+  }
+}
+
+
+}  // namespace cnf

@@ -1,28 +1,31 @@
-// tcgen05 / TMEM kernels for the hidden-layer chain of the FiLM-SIREN decoder (sm_100a).
+// Generic tcgen05 / TMEM kernels for the hidden-layer chain of the FiLM-SIREN decoder (sm_100a): H = 256, 384
+// (H = 128 has its own TMEM-resident kernels in tc2_kernels.cuh).
 //
-// One CTA decodes 128-point tiles of one frame at a time:
-//   warps 0-3  (128 threads) "epilogue": thread r owns query point r of the tile (TMEM lane r).
-//              Layer 0 (K = cin) on CUDA cores; for each hidden layer: tcgen05.ld the fp32
-//              accumulator, add the FiLM shift, range-reduce, MUFU sin, split into bf16 hi/lo (or
-//              fp16) and write the next layer's A operand into shared memory in the K-major
-//              SWIZZLE_128B layout; last layer: dot with the output head in registers.
-//   warp 4     one elected thread issues tcgen05.mma (M=128, N=128, K=16) for every
-//              (row block, K slab, hi/lo pass) of the layer, accumulators in TMEM.
-//   warp 5     one elected thread streams the pre-swizzled 16 KiB weight stages from L2 into a
-//              shared-memory ring with 1-D bulk TMA copies (cp.async.bulk + mbarrier tx bytes).
-// Hand-shakes: b_full/b_empty per ring slot, a_full (A operand written, 128 arrivals),
-// d_full (layer's MMAs complete, tcgen05.commit).
+// One CTA decodes 128-point tiles of one frame at a time; the A operand (activations of the previous layer, bf16 hi/lo
+// or fp16) lives in shared memory in the UMMA K-major SWIZZLE_128B layout:
+//   warps 0-15  "activation" warps: warp = 4*cg + wq; thread (wq, lane) owns query point wq*32+lane (TMEM lane), column
+//               group cg owns columns [cg*H/4, (cg+1)*H/4).  Layer 0 (K = cin) on CUDA cores; per hidden layer
+//               tcgen05.ld of the fp32 accumulator 16 columns at a time, + FiLM shift, MUFU sin, split into bf16 hi/lo
+//               (or fp16), 16-byte conflict-free st.shared into the next layer's A operand; last layer: partial dot
+//               with the output head, the four column groups meet in shared memory.
+//   warp 16     MMA issuer: the whole warp walks the schedule, one elected lane issues tcgen05.mma (M=128, N=128, K=16,
+//               both operands from shared memory) for every (row block, K slab, hi/lo pass); accumulators in TMEM.
+//   warp 17     one lane streams the pre-swizzled 16 KiB weight stages from L2 with 1-D bulk TMA copies.
+// Hand-shakes: b_full/b_empty per ring slot, a_full (A operand written, 512 arrivals), d_full (layer's MMAs done).
+// Sixteen activation warps (four per SM sub-partition) bring the epilogue to the MUFU bound; MMA and epilogue of a tile
+// do not overlap here (a second 128 x H operand does not fit: 2 x 192 KB at H = 384).
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "layout.cuh"
 #include "ptx.cuh"
+#include "tc_common.cuh"
 
 namespace cnf {
 
-constexpr int kTcThreads = 192;
-constexpr int kTcMaxStages = 12;
+constexpr int kTcEpiWarps = 16;
+constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
 
 template <int H, int PREC>
 struct TcCfg {
@@ -33,8 +36,10 @@ struct TcCfg {
   static constexpr int kAPartBytes = kSlabs * kTileM * 128;  // one 128 x H 16-bit operand
   static constexpr int kABytes = kParts * kAPartBytes;
   static constexpr int kStagesPerLayer = kNBlocks * kSlabs * kParts;
+  static constexpr int kColsPerGroup = H / 4;  // columns per activation column group
   static constexpr uint32_t kTmemCols = H <= 128 ? 128u : (H <= 256 ? 256u : 512u);
   static constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, kStageRows);
+  static_assert(kColsPerGroup % 16 == 0, "column groups are processed 16 columns at a time");
 };
 
 struct TcSmemTail {  // lives after the A operand and the weight ring
@@ -98,15 +103,16 @@ __device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_ad
   __syncwarp();
 }
 
-// Convert 32 activations (columns c0..c0+31 of this thread's row) to the 16-bit operand format and
-// store them into the A operand (K-major SWIZZLE_128B): 4 chunks of 16 bytes per part.
+// Convert 16 activations (columns c0..c0+15 of this thread's row) to the 16-bit operand format and store them into
+// the A operand (K-major SWIZZLE_128B): 2 chunks of 16 bytes per part.  Eight consecutive rows hit eight different
+// 16-byte chunk positions, so the stores are bank-conflict free.
 template <int H, int PREC>
-__device__ __forceinline__ void tc_store_a(uint8_t* a_smem, int row, int c0, const float (&h)[32]) {
+__device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, int row, int c0, const float (&h)[16]) {
   using C = TcCfg<H, PREC>;
   uint8_t* rowp = a_smem + (c0 / kSlabK) * (kTileM * 128) + row * 128;
   const uint32_t cbase = (c0 % kSlabK) / 8;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 2; ++q) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -124,32 +130,45 @@ __device__ __forceinline__ void tc_store_a(uint8_t* a_smem, int row, int c0, con
   }
 }
 
-template <bool REDUCE>
-__device__ __forceinline__ void sin_cos_of(float z, bool want_cos, float& s, float& c) {
-  const float r = REDUCE ? ptx::reduce_2pi(z) : z;
-  s = ptx::sin_approx(r);
-  c = want_cos ? ptx::cos_approx(r) : 0.f;
+// Common prologue: barriers, TMEM allocation.  Returns the TMEM base.
+template <int H, int PREC>
+__device__ __forceinline__ uint32_t tc_setup(TcSmemTail* tail, int num_stages, int warp) {
+  using C = TcCfg<H, PREC>;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      ptx::mbar_init(&tail->b_full[s], 1);
+      ptx::mbar_init(&tail->b_empty[s], 1);
+    }
+    ptx::mbar_init(&tail->a_full, kTcEpiWarps * 32);
+    ptx::mbar_init(&tail->d_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == kTcEpiWarps) {
+    ptx::tmem_alloc(&tail->tmem_base, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  return tail->tmem_base;
 }
 
-__device__ __forceinline__ void stash_store_f16(__half* dst, const float (&c)[32]) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t w[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) w[e] = ptx::pack_f16x2(c[q * 8 + 2 * e], c[q * 8 + 2 * e + 1]);
-    d4[q] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
+// Activation warps wait for the layer's accumulator: one warp polls the mbarrier, the others sleep on a named barrier.
+__device__ __forceinline__ void tc_wait_d_full(TcSmemTail* tail, int warp, uint32_t& d_phase) {
+  if (warp == 0) ptx::mbar_wait(&tail->d_full, d_phase);
+  d_phase ^= 1u;
+  ptx::bar_sync(1, kTcEpiWarps * 32);
+  ptx::tc_fence_after();
 }
 
 // ------------------------------------------------------------------ forward
 template <int H, int PREC, bool STASH, bool REDUCE>
-__global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
-                                                                const float* __restrict__ coords,
-                                                                int64_t coord_frame_stride,
-                                                                const float* __restrict__ shift,
-                                                                float* __restrict__ out, __half* __restrict__ stash,
-                                                                int64_t T, int64_t P, int num_stages) {
+__global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
+                                                                   const float* __restrict__ coords,
+                                                                   int64_t coord_frame_stride,
+                                                                   const float* __restrict__ shift,
+                                                                   float* __restrict__ out, __half* __restrict__ stash,
+                                                                   int64_t T, int64_t P, int num_stages) {
   using C = TcCfg<H, PREC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -163,32 +182,18 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
   const int64_t PB = (P + kTileM - 1) / kTileM;
   const int64_t tiles = T * PB;
   const int64_t SH = (int64_t)(nl + 1) * H;
+  const uint32_t tmem_base = tc_setup<H, PREC>(tail, num_stages, warp);
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < num_stages; ++s) {
-      ptx::mbar_init(&tail->b_full[s], 1);
-      ptx::mbar_init(&tail->b_empty[s], 1);
-    }
-    ptx::mbar_init(&tail->a_full, 128);
-    ptx::mbar_init(&tail->d_full, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 4) {
-    ptx::tmem_alloc(&tail->tmem_base, C::kTmemCols);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = tail->tmem_base;
-
-  if (warp < 4) {
-    // ===================== epilogue / activation warps =====================
-    const int row = threadIdx.x;
+  if (warp < kTcEpiWarps) {
+    // ===================== activation warps =====================
+    const int cg = warp / 4, wq = warp % 4;
+    const int row = wq * 32 + lane;
+    const int col_lo = cg * C::kColsPerGroup, col_hi = col_lo + C::kColsPerGroup;
     const float* w_first = reinterpret_cast<const float*>(packed + lay.w_first);
     const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
     const float* b_out = reinterpret_cast<const float*>(packed + lay.b_out);
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(wq * 32) << 16);
+    float4* y_part = reinterpret_cast<float4*>(a_smem);  // [3][128] partial head sums; A is free after the last layer
     uint32_t d_phase = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
@@ -201,25 +206,25 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
         for (int j = 0; j < 4; ++j)
           if (j < cin) x[j] = cp[j];
       }
-      __half* st_row = STASH ? stash + (t * P + (valid ? p : 0)) * SH : nullptr;
+      __half* st_row = (STASH && valid) ? stash + (t * P + p) * SH : nullptr;
 
       // ---- layer 0: K = cin on CUDA cores, always range-reduced (|arg| reaches tens of radians)
 #pragma unroll 1
-      for (int c0 = 0; c0 < H; c0 += 32) {
-        float h[32], cs[32];
+      for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
+        float h[16];
+        [[maybe_unused]] float cs[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           float z = __ldg(sh + c0 + j);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (i < cin) z = fmaf(__ldg(w_first + (c0 + j) * cin + i), x[i], z);
-          sin_cos_of<true>(z, STASH, h[j], cs[j]);
+          const float r = ptx::reduce_2pi(z);
+          h[j] = ptx::sin_approx(r);
+          if (STASH) cs[j] = ptx::cos_approx(r);
         }
-        tc_store_a<H, PREC>(a_smem, row, c0, h);
-        if (STASH) {
-          if (valid) stash_store_f16(st_row + c0, cs);
-          __syncwarp();
-        }
+        tc_store_a16<H, PREC>(a_smem, row, c0, h);
+        if (STASH) tc_stash16(st_row ? st_row + c0 : nullptr, cs);
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
@@ -229,33 +234,24 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
 #pragma unroll 1
       for (int l = 1; l <= nl; ++l) {
         const float* shl = sh + (size_t)l * H;
-        ptx::mbar_wait(&tail->d_full, d_phase);
-        d_phase ^= 1u;
-        ptx::tc_fence_after();
+        tc_wait_d_full(tail, warp, d_phase);
         const bool last = (l == nl);
 #pragma unroll 1
-        for (int c0 = 0; c0 < H; c0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tmem_row + c0, v);
+        for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(tmem_row + c0, v);
           ptx::tmem_wait_ld();
-          float h[32], cs[32];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(shl + c0) + q);
-            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              sin_cos_of<REDUCE>(__uint_as_float(v[q * 4 + e]) + sv[e], STASH, h[q * 4 + e], cs[q * 4 + e]);
-          }
+          float h[16];
+          tc_sines16<REDUCE, STASH>(v, shl + c0, h, st_row ? st_row + (size_t)l * H + c0 : nullptr);
           if (!last) {
-            tc_store_a<H, PREC>(a_smem, row, c0, h);
+            tc_store_a16<H, PREC>(a_smem, row, c0, h);
           } else {
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
               if (o >= cout) continue;
               float acc = y[o];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
+              for (int q = 0; q < 4; ++q) {
                 const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_out + (size_t)o * H + c0) + q);
                 acc = fmaf(w4.x, h[q * 4 + 0], acc);
                 acc = fmaf(w4.y, h[q * 4 + 1], acc);
@@ -265,40 +261,44 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
               y[o] = acc;
             }
           }
-          if (STASH) {
-            if (valid) stash_store_f16(st_row + (size_t)l * H + c0, cs);
-            __syncwarp();
-          }
         }
+        ptx::tc_fence_before();
         if (!last) {
-          ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(&tail->a_full);
         }
       }
-      if (valid) {
+      // ---- head: the four column groups meet in shared memory (the A operand is free until the next tile's layer 0)
+      if (cg > 0) y_part[(cg - 1) * kTileM + row] = make_float4(y[0], y[1], y[2], y[3]);
+      ptx::bar_sync(1, kTcEpiWarps * 32);
+      if (cg == 0 && valid) {
+        float ys[4] = {y[0], y[1], y[2], y[3]};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4 yp = y_part[k * kTileM + row];
+          ys[0] += yp.x; ys[1] += yp.y; ys[2] += yp.z; ys[3] += yp.w;
+        }
         float* op = out + (t * P + p) * cout;
 #pragma unroll
         for (int o = 0; o < 4; ++o)
-          if (o < cout) op[o] = y[o] + __ldg(b_out + o);
+          if (o < cout) op[o] = ys[o] + __ldg(b_out + o);
       }
-      __syncwarp();  // rows past P skipped the store: reconverge before the next tile's warp-aligned instructions
+      __syncwarp();
+      ptx::bar_sync(1, kTcEpiWarps * 32);  // partial sums consumed before the next tile's layer 0 overwrites them
     }
     ptx::tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == kTcEpiWarps) {
     // ===================== MMA issuer (whole warp, one elected lane issues) =====================
-    {
-      const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
-      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      int slot = 0;
-      uint32_t b_phase = 0, a_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        for (int l = 1; l <= nl; ++l) {
-          ptx::mbar_wait(&tail->a_full, a_phase);
-          a_phase ^= 1u;
-          ptx::tc_fence_after();
-          tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
-        }
+    const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int slot = 0;
+    uint32_t b_phase = 0, a_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int l = 1; l <= nl; ++l) {
+        ptx::mbar_wait(&tail->a_full, a_phase);
+        a_phase ^= 1u;
+        ptx::tc_fence_after();
+        tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
       }
     }
     __syncwarp();
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kTcEpiWarps) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }
@@ -333,27 +333,12 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_forward_ker
 // ------------------------------------------------------------------ backward (to the FiLM shifts)
 // delta_nl = (gout * W_out) .* cos_nl ; for l = nl..1: delta_{l-1} = (delta_l * w0*W_l) .* cos_{l-1};
 // gshift[t, l, n] += sum over the tile's points of delta_l[., n].  Always bf16 hi/lo split operands.
-__device__ __forceinline__ void colsum_to_global(float (&v)[32], int lane, float* dst) {
-  // transpose-reduce: after 5 rounds lane j holds the sum over the warp's 32 rows of column j
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = upper ? v[i] : v[i + off];
-      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
-      v[i] = (upper ? v[i + off] : v[i]) + recv;
-    }
-  }
-  atomicAdd(dst + lane, v[0]);
-}
-
 template <int H>
-__global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_backward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
-                                                                 const float* __restrict__ gout,
-                                                                 const __half* __restrict__ stash,
-                                                                 float* __restrict__ gshift, int64_t T, int64_t P,
-                                                                 int num_stages) {
+__global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
+                                                                    const float* __restrict__ gout,
+                                                                    const __half* __restrict__ stash,
+                                                                    float* __restrict__ gshift, int64_t T, int64_t P,
+                                                                    int num_stages) {
   constexpr int PREC = CNF_PREC_BF16X3;
   using C = TcCfg<H, PREC>;
   extern __shared__ uint8_t smem_raw[];
@@ -368,34 +353,20 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_backward_ke
   const int64_t PB = (P + kTileM - 1) / kTileM;
   const int64_t tiles = T * PB;
   const int64_t SH = (int64_t)(nl + 1) * H;
+  const uint32_t tmem_base = tc_setup<H, PREC>(tail, num_stages, warp);
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < num_stages; ++s) {
-      ptx::mbar_init(&tail->b_full[s], 1);
-      ptx::mbar_init(&tail->b_empty[s], 1);
-    }
-    ptx::mbar_init(&tail->a_full, 128);
-    ptx::mbar_init(&tail->d_full, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 4) {
-    ptx::tmem_alloc(&tail->tmem_base, C::kTmemCols);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = tail->tmem_base;
-
-  if (warp < 4) {
-    const int row = threadIdx.x;
+  if (warp < kTcEpiWarps) {
+    const int cg = warp / 4, wq = warp % 4;
+    const int row = wq * 32 + lane;
+    const int col_lo = cg * C::kColsPerGroup, col_hi = col_lo + C::kColsPerGroup;
     const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(wq * 32) << 16);
     uint32_t d_phase = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
       const bool valid = p < P;
       float* gs = gshift + t * SH;
+      // rows past P read the frame's row 0: their delta is exactly zero (their dL/dy is), and the warp stays converged
       const __half* st_row = stash + (t * P + (valid ? p : 0)) * SH;
       float gy[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
@@ -403,39 +374,21 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_backward_ke
         for (int o = 0; o < 4; ++o)
           if (o < cout) gy[o] = gout[(t * P + p) * cout + o];
       }
-
-      // rows past P read the frame's row 0 (st_row is clamped): their delta is exactly zero because their dL/dy is,
-      // and the warp stays converged for the warp-aligned tcgen05 instructions that follow
-      auto load_cos = [&](int l, int c0, float (&c)[32]) {
-        const uint4* s4 = reinterpret_cast<const uint4*>(st_row + (size_t)l * H + c0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 w = __ldg(s4 + q);
-          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[e]));
-            c[q * 8 + 2 * e] = f.x;
-            c[q * 8 + 2 * e + 1] = f.y;
-          }
-        }
-      };
-
       // ---- seed: delta at the last sine layer
 #pragma unroll 1
-      for (int c0 = 0; c0 < H; c0 += 32) {
-        float cs[32], dl[32];
-        load_cos(nl, c0, cs);
+      for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
+        float cs[16], dl[16];
+        tc_load_cos16(st_row + (size_t)nl * H + c0, cs);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           float g = 0.f;
 #pragma unroll
           for (int o = 0; o < 4; ++o)
             if (o < cout) g = fmaf(gy[o], __ldg(w_out + (size_t)o * H + c0 + j), g);
           dl[j] = g * cs[j];
         }
-        tc_store_a<H, PREC>(a_smem, row, c0, dl);
-        colsum_to_global(dl, lane, gs + (size_t)nl * H + c0);
+        tc_store_a16<H, PREC>(a_smem, row, c0, dl);
+        tc_colsum16_to_global(dl, lane, gs + (size_t)nl * H + c0);
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
@@ -443,20 +396,18 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_backward_ke
 
 #pragma unroll 1
       for (int l = nl; l >= 1; --l) {
-        ptx::mbar_wait(&tail->d_full, d_phase);
-        d_phase ^= 1u;
-        ptx::tc_fence_after();
+        tc_wait_d_full(tail, warp, d_phase);
 #pragma unroll 1
-        for (int c0 = 0; c0 < H; c0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(tmem_row + c0, v);
-          float cs[32], dl[32];
-          load_cos(l - 1, c0, cs);
+        for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(tmem_row + c0, v);
+          float cs[16], dl[16];
+          tc_load_cos16(st_row + (size_t)(l - 1) * H + c0, cs);
           ptx::tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
-          if (l > 1) tc_store_a<H, PREC>(a_smem, row, c0, dl);
-          colsum_to_global(dl, lane, gs + (size_t)(l - 1) * H + c0);
+          for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
+          if (l > 1) tc_store_a16<H, PREC>(a_smem, row, c0, dl);
+          tc_colsum16_to_global(dl, lane, gs + (size_t)(l - 1) * H + c0);
         }
         ptx::tc_fence_before();
         if (l > 1) {
@@ -465,19 +416,17 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_backward_ke
         }
       }
     }
-  } else if (warp == 4) {
-    {
-      const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
-      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      int slot = 0;
-      uint32_t b_phase = 0, a_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        for (int l = nl; l >= 1; --l) {
-          ptx::mbar_wait(&tail->a_full, a_phase);
-          a_phase ^= 1u;
-          ptx::tc_fence_after();
-          tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
-        }
+  } else if (warp == kTcEpiWarps) {
+    const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int slot = 0;
+    uint32_t b_phase = 0, a_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int l = nl; l >= 1; --l) {
+        ptx::mbar_wait(&tail->a_full, a_phase);
+        a_phase ^= 1u;
+        ptx::tc_fence_after();
+        tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
       }
     }
     __syncwarp();
@@ -502,7 +451,7 @@ __global__ void __launch_bounds__(kTcThreads, (H <= 128 ? 2 : 1)) tc_backward_ke
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kTcEpiWarps) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }

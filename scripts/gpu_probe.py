@@ -114,6 +114,9 @@ if __name__ == "__main__":
         for prec in ("bf16x3", "fp16"):
             timeit("case4", 16, 16384, prec)
         timeit("case1", 16, 16384, "fp32", iters=2)
+    if what == "case2":
+        for prec in ("bf16x3", "fp16"):
+            timeit("case2", 32, 16384, prec)
     if what in ("all", "dps"):
         for prec in ("bf16x3", "fp16", "fp32"):
             time_dps("case1", 64, 16384, prec)
