@@ -33,11 +33,17 @@ struct TcCfg {
   static constexpr int kParts = kSplit ? 2 : 1;
   static constexpr int kSlabs = H / kSlabK;
   static constexpr int kNBlocks = H / kStageRows;
-  static constexpr int kAPartBytes = kSlabs * kTileM * 128;  // one 128 x H 16-bit operand
+  // The first kATmemBlocks 128-column blocks of the A operand live in the TMEM columns the accumulator leaves free
+  // ([H, 512): packed hi 64 columns + lo 64 columns per block) and are read by the MMA from TMEM (85 clk per MMA
+  // instead of 116 from shared memory); the rest of A is in shared memory.  H=256: all of A; H=384: one third.
+  static constexpr int kATmemBlocks = ((512 - H) / 128) < (H / 128) ? ((512 - H) / 128) : (H / 128);
+  static constexpr int kATmemCols = kATmemBlocks * 128;       // activation columns (= K range) resident in TMEM
+  static constexpr int kASmemSlabs = kSlabs - 2 * kATmemBlocks;
+  static constexpr int kAPartBytes = kASmemSlabs * kTileM * 128;  // shared-memory part of one 16-bit operand
   static constexpr int kABytes = kParts * kAPartBytes;
   static constexpr int kStagesPerLayer = kNBlocks * kSlabs * kParts;
   static constexpr int kColsPerGroup = H / 4;  // columns per activation column group
-  static constexpr uint32_t kTmemCols = H <= 128 ? 128u : (H <= 256 ? 256u : 512u);
+  static constexpr uint32_t kTmemCols = (H + kATmemCols) <= 256 ? 256u : 512u;
   static constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, kStageRows);
   static_assert(kColsPerGroup % 16 == 0, "column groups are processed 16 columns at a time");
 };
@@ -52,8 +58,8 @@ struct TcSmemTail {  // lives after the A operand and the weight ring
 
 template <int H, int PREC>
 __host__ __device__ constexpr size_t tc_smem_bytes(int num_stages) {
-  return 1024 /*alignment slack*/ + (size_t)TcCfg<H, PREC>::kABytes + (size_t)num_stages * kStageBytes +
-         sizeof(TcSmemTail);
+  return 1024 /*alignment slack*/ + (size_t)TcCfg<H, PREC>::kABytes + (size_t)num_stages * kStageBytes + 256 +
+         (TcCfg<H, PREC>::kABytes >= 3 * kTileM * 16 ? 0 : 3 * kTileM * 16);
 }
 
 // ------------------------------------------------------------------ shared pieces
@@ -68,17 +74,29 @@ __device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_ad
   for (int nb = 0; nb < C::kNBlocks; ++nb) {
 #pragma unroll 1
     for (int ks = 0; ks < C::kSlabs; ++ks) {
-      const uint64_t a_hi = ptx::make_desc_k_sw128(a_addr + ks * (kTileM * 128));
-      const uint64_t a_lo = ptx::make_desc_k_sw128(a_addr + C::kAPartBytes + ks * (kTileM * 128));
+      const bool a_in_tmem = ks < 2 * C::kATmemBlocks;
+      // A from TMEM: K slab ks = columns [64*ks, 64*ks+64) of block ks/2 -> 8 packed columns per K=16 step
+      const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
+      const int ss = a_in_tmem ? 0 : ks - 2 * C::kATmemBlocks;
+      const uint64_t a_hi = ptx::make_desc_k_sw128(a_addr + ss * (kTileM * 128));
+      const uint64_t a_lo = ptx::make_desc_k_sw128(a_addr + C::kAPartBytes + ss * (kTileM * 128));
       // weights, high part (or the only part): pairs with a_hi and a_lo
       ptx::mbar_wait(&tail->b_full[slot], phase);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+        if (a_in_tmem) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {  // 4 x K=16 inside the 128-byte row: +32 bytes = +2 in the address field
-          ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, (ks | kk) != 0);
-          if (C::kSplit) ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_lo + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
+          for (int kk = 0; kk < 4; ++kk) {
+            ptx::umma_f16_ts(tmem_d + nb * kStageRows, at_hi + kk * 8, b + 2 * kk, C::kIdesc, (ks | kk) != 0);
+            if (C::kSplit) ptx::umma_f16_ts(tmem_d + nb * kStageRows, at_hi + 64 + kk * 8, b + 2 * kk, C::kIdesc, 1u);
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {  // 4 x K=16 inside the 128-byte row: +32 bytes = +2 in the address field
+            ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, (ks | kk) != 0);
+            if (C::kSplit) ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_lo + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
+          }
         }
         ptx::umma_commit(&tail->b_empty[slot]);
       }
@@ -89,9 +107,15 @@ __device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_ad
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+          if (a_in_tmem) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
+            for (int kk = 0; kk < 4; ++kk)
+              ptx::umma_f16_ts(tmem_d + nb * kStageRows, at_hi + kk * 8, b + 2 * kk, C::kIdesc, 1u);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
+          }
           ptx::umma_commit(&tail->b_empty[slot]);
         }
         __syncwarp();
@@ -107,10 +131,29 @@ __device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_ad
 // the A operand (K-major SWIZZLE_128B): 2 chunks of 16 bytes per part.  Eight consecutive rows hit eight different
 // 16-byte chunk positions, so the stores are bank-conflict free.
 template <int H, int PREC>
-__device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, int row, int c0, const float (&h)[16]) {
+__device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, uint32_t tmem_row, int row, int c0,
+                                             const float (&h)[16]) {
   using C = TcCfg<H, PREC>;
-  uint8_t* rowp = a_smem + (c0 / kSlabK) * (kTileM * 128) + row * 128;
-  const uint32_t cbase = (c0 % kSlabK) / 8;
+  if (c0 < C::kATmemCols) {  // this K range of the operand is TMEM-resident (warp-uniform branch)
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x0 = h[2 * e], x1 = h[2 * e + 1];
+      if (C::kSplit) {
+        hi[e] = ptx::pack_bf16x2(x0, x1);
+        lo[e] = ptx::pack_bf16x2(x0 - ptx::bf16lo_to_f32(hi[e]), x1 - ptx::bf16hi_to_f32(hi[e]));
+      } else {
+        hi[e] = ptx::pack_f16x2(x0, x1);
+      }
+    }
+    const uint32_t ta = tmem_row + H + (c0 / 128) * 128 + (c0 % 128) / 2;
+    ptx::tmem_st_32x32b_x8(ta, hi);
+    if (C::kSplit) ptx::tmem_st_32x32b_x8(ta + 64, lo);
+    return;
+  }
+  const int cs = c0 - C::kATmemCols;
+  uint8_t* rowp = a_smem + (cs / kSlabK) * (kTileM * 128) + row * 128;
+  const uint32_t cbase = (cs % kSlabK) / 8;
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     uint32_t hi[4], lo[4];
@@ -193,7 +236,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
     const float* b_out = reinterpret_cast<const float*>(packed + lay.b_out);
     const uint32_t tmem_row = tmem_base + ((uint32_t)(wq * 32) << 16);
-    float4* y_part = reinterpret_cast<float4*>(a_smem);  // [3][128] partial head sums; A is free after the last layer
+    // [3][128] partial head sums: in the A operand's shared memory when there is one (free after the last layer),
+    // else (all of A in TMEM) in a dedicated 6 KiB area behind the barriers
+    float4* y_part = C::kABytes >= 3 * kTileM * 16 ? reinterpret_cast<float4*>(a_smem)
+                                                   : reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tail) + 256);
     uint32_t d_phase = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
@@ -223,9 +269,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
           h[j] = ptx::sin_approx(r);
           if (STASH) cs[j] = ptx::cos_approx(r);
         }
-        tc_store_a16<H, PREC>(a_smem, row, c0, h);
+        tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
         if (STASH) tc_stash16(st_row ? st_row + c0 : nullptr, cs);
       }
+      ptx::tmem_wait_st();
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&tail->a_full);
@@ -244,7 +291,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
           float h[16];
           tc_sines16<REDUCE, STASH>(v, shl + c0, h, st_row ? st_row + (size_t)l * H + c0 : nullptr);
           if (!last) {
-            tc_store_a16<H, PREC>(a_smem, row, c0, h);
+            tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
           } else {
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
@@ -262,10 +309,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
             }
           }
         }
-        ptx::tc_fence_before();
         if (!last) {
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(&tail->a_full);
+        } else {
+          ptx::tc_fence_before();
         }
       }
       // ---- head: the four column groups meet in shared memory (the A operand is free until the next tile's layer 0)
@@ -387,9 +437,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
             if (o < cout) g = fmaf(gy[o], __ldg(w_out + (size_t)o * H + c0 + j), g);
           dl[j] = g * cs[j];
         }
-        tc_store_a16<H, PREC>(a_smem, row, c0, dl);
+        tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, dl);
         tc_colsum16_to_global(dl, lane, gs + (size_t)nl * H + c0);
       }
+      ptx::tmem_wait_st();
       ptx::tc_fence_before();
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&tail->a_full);
@@ -406,13 +457,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
           ptx::tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
-          if (l > 1) tc_store_a16<H, PREC>(a_smem, row, c0, dl);
+          if (l > 1) tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, dl);
           tc_colsum16_to_global(dl, lane, gs + (size_t)(l - 1) * H + c0);
         }
-        ptx::tc_fence_before();
         if (l > 1) {
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(&tail->a_full);
+        } else {
+          ptx::tc_fence_before();
         }
       }
     }
