@@ -85,6 +85,8 @@ int make_tc_plan(const DeviceInfo& di, int64_t tiles, TcPlan* plan) {
   if (stages > cnf::kTcMaxStages) stages = cnf::kTcMaxStages;
   const int forced = env_int("CNF_TC_STAGES", 0);
   if (forced >= 2 && forced <= stages) stages = forced;
+  stages -= stages % C::kNBlocks;  // the MMA warp consumes the ring in groups of kNBlocks adjacent slots
+  if (stages < C::kNBlocks) return fail(CNF_ERR_UNSUPPORTED, "weight ring too small for H=%d", H);
   plan->stages = stages;
   plan->ctas_per_sm = 1;
   plan->smem = cnf::tc_smem_bytes<H, PREC>(stages);

@@ -53,15 +53,17 @@ __global__ void pack_tc_kernel(cnf_dims d, const float* __restrict__ params, flo
   const size_t elems_per_stage = kStageRows * kSlabK;
   const size_t total = nl * spl * elems_per_stage;
   uint8_t* base = packed + (mode == 0 ? lay.tc_fwd_x3 : mode == 1 ? lay.tc_fwd_h : lay.tc_bwd_x3);
-  const size_t kslabs = H / kSlabK;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t l = i / (spl * elems_per_stage);
     const size_t s = (i / elems_per_stage) % spl;
     const uint32_t e = (uint32_t)(i % elems_per_stage);
     const uint32_t r = e / kSlabK, kk = e % kSlabK;
-    const size_t part = s % parts;
-    const size_t ks = (s / parts) % kslabs;
-    const size_t nb = (s / parts) / kslabs;
+    // stage order = consumption order of the MMA warps: K slab, then hi/lo part, then 128-row block (innermost, so the
+    // row blocks of one (slab, part) are adjacent in the ring and can feed a single N=256 MMA)
+    const size_t nblocks = H / kStageRows;
+    const size_t nb = s % nblocks;
+    const size_t part = (s / nblocks) % parts;
+    const size_t ks = s / (nblocks * parts);
     const size_t n = nb * kStageRows + r;
     const size_t k = ks * kSlabK + kk;
     const size_t src = (mode == 2) ? (k * H + n) : (n * H + k);

@@ -70,57 +70,55 @@ template <int H, int PREC>
 __device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_addr, uint32_t tmem_d, TcSmemTail* tail,
                                                int num_stages, int& slot, uint32_t& phase) {
   using C = TcCfg<H, PREC>;
+  constexpr int NB = C::kNBlocks;
+  // One weight "group" = the NB adjacent ring slots holding all 128-row blocks of one (K slab, hi/lo part).  Row blocks
+  // 0 and 1 are contiguous in shared memory, so they feed ONE N=256 MMA (145/175 clk instead of 2 x 85/116); a third
+  // block (H=384) gets an N=128 MMA into the next accumulator columns, which also interleaves independent accumulators.
+  constexpr uint32_t kIdescWide = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kTileM, NB >= 2 ? 256 : 128);
+  constexpr uint32_t kIdescTail = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kTileM, 128);
 #pragma unroll 1
-  for (int nb = 0; nb < C::kNBlocks; ++nb) {
-#pragma unroll 1
-    for (int ks = 0; ks < C::kSlabs; ++ks) {
-      const bool a_in_tmem = ks < 2 * C::kATmemBlocks;
-      // A from TMEM: K slab ks = columns [64*ks, 64*ks+64) of block ks/2 -> 8 packed columns per K=16 step
-      const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
-      const int ss = a_in_tmem ? 0 : ks - 2 * C::kATmemBlocks;
-      const uint64_t a_hi = ptx::make_desc_k_sw128(a_addr + ss * (kTileM * 128));
-      const uint64_t a_lo = ptx::make_desc_k_sw128(a_addr + C::kAPartBytes + ss * (kTileM * 128));
-      // weights, high part (or the only part): pairs with a_hi and a_lo
-      ptx::mbar_wait(&tail->b_full[slot], phase);
+  for (int ks = 0; ks < C::kSlabs; ++ks) {
+    const bool a_in_tmem = ks < 2 * C::kATmemBlocks;
+    // A from TMEM: K slab ks = columns [64*ks, 64*ks+64) of block ks/2 -> 8 packed columns per K=16 step
+    const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
+    const int ss = a_in_tmem ? 0 : ks - 2 * C::kATmemBlocks;
+    const uint64_t a_hi = ptx::make_desc_k_sw128(a_addr + ss * (kTileM * 128));
+    const uint64_t a_lo = ptx::make_desc_k_sw128(a_addr + C::kAPartBytes + ss * (kTileM * 128));
+#pragma unroll
+    for (int part = 0; part < C::kParts; ++part) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {  // the group's slots never wrap: num_stages is a multiple of NB
+        ptx::mbar_wait(&tail->b_full[slot + j], phase);
+      }
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
-        if (a_in_tmem) {
+        const uint64_t b2 = ptx::make_desc_k_sw128(ring_addr + (slot + 2) * kStageBytes);  // third row block (NB == 3)
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            ptx::umma_f16_ts(tmem_d + nb * kStageRows, at_hi + kk * 8, b + 2 * kk, C::kIdesc, (ks | kk) != 0);
-            if (C::kSplit) ptx::umma_f16_ts(tmem_d + nb * kStageRows, at_hi + 64 + kk * 8, b + 2 * kk, C::kIdesc, 1u);
-          }
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // 4 x K=16 inside the 128-byte row: +32 bytes = +2 in the address field
-            ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, (ks | kk) != 0);
-            if (C::kSplit) ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_lo + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
+        for (int kk = 0; kk < 4; ++kk) {  // 4 x K=16 inside the 128-byte row: +32 bytes = +2 in the address field
+          const uint32_t first = (part == 0) ? (uint32_t)((ks | kk) != 0) : 1u;
+          if (a_in_tmem) {
+            ptx::umma_f16_ts(tmem_d, at_hi + kk * 8, b + 2 * kk, kIdescWide, first);
+            if (NB == 3) ptx::umma_f16_ts(tmem_d + 256, at_hi + kk * 8, b2 + 2 * kk, kIdescTail, first);
+            if (C::kSplit && part == 0) {
+              ptx::umma_f16_ts(tmem_d, at_hi + 64 + kk * 8, b + 2 * kk, kIdescWide, 1u);
+              if (NB == 3) ptx::umma_f16_ts(tmem_d + 256, at_hi + 64 + kk * 8, b2 + 2 * kk, kIdescTail, 1u);
+            }
+          } else {
+            ptx::umma_f16_ss(tmem_d, a_hi + 2 * kk, b + 2 * kk, kIdescWide, first);
+            if (NB == 3) ptx::umma_f16_ss(tmem_d + 256, a_hi + 2 * kk, b2 + 2 * kk, kIdescTail, first);
+            if (C::kSplit && part == 0) {
+              ptx::umma_f16_ss(tmem_d, a_lo + 2 * kk, b + 2 * kk, kIdescWide, 1u);
+              if (NB == 3) ptx::umma_f16_ss(tmem_d + 256, a_lo + 2 * kk, b2 + 2 * kk, kIdescTail, 1u);
+            }
           }
         }
-        ptx::umma_commit(&tail->b_empty[slot]);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) ptx::umma_commit(&tail->b_empty[slot + j]);
       }
       __syncwarp();
-      if (++slot == num_stages) { slot = 0; phase ^= 1u; }
-      if (C::kSplit) {  // weights, low part: pairs with a_hi only
-        ptx::mbar_wait(&tail->b_full[slot], phase);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
-          if (a_in_tmem) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              ptx::umma_f16_ts(tmem_d + nb * kStageRows, at_hi + kk * 8, b + 2 * kk, C::kIdesc, 1u);
-          } else {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              ptx::umma_f16_ss(tmem_d + nb * kStageRows, a_hi + 2 * kk, b + 2 * kk, C::kIdesc, 1u);
-          }
-          ptx::umma_commit(&tail->b_empty[slot]);
-        }
-        __syncwarp();
-        if (++slot == num_stages) { slot = 0; phase ^= 1u; }
-      }
+      slot += NB;
+      if (slot >= num_stages) { slot = 0; phase ^= 1u; }
     }
   }
   if (ptx::elect_one()) ptx::umma_commit(&tail->d_full);
