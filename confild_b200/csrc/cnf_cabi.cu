@@ -312,7 +312,9 @@ int cnf_stash_bytes(const cnf_dims* dims, int precision, int64_t T, int64_t P, s
     case CNF_PREC_FP16: esize = 2; break;
     default: return fail(CNF_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
   }
-  *bytes = (size_t)T * (size_t)P * (size_t)(dims->nl + 1) * (size_t)dims->H * esize;
+  // fp32 path: [t][p][layer][column]; tensor-core paths: tile-major with rows padded to whole 128-point tiles
+  const size_t rows = precision == CNF_PREC_FP32 ? (size_t)P : (size_t)((P + cnf::kTileM - 1) / cnf::kTileM) * cnf::kTileM;
+  *bytes = (size_t)T * rows * (size_t)(dims->nl + 1) * (size_t)dims->H * esize;
   return CNF_OK;
 }
 

@@ -92,7 +92,7 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
   ptx::tmem_ld_32x32b_x16(lane_base + col0, v[0]);
   ptx::tmem_wait_ld();
   ptx::tmem_ld_32x32b_x16(lane_base + col0 + 16, v[1]);
-  tc_sines16<REDUCE, STASH>(v[0], sbuf + col0, hnext, (STASH && stash_l) ? stash_l + col0 : nullptr);
+  tc_sines16<REDUCE, STASH>(v[0], sbuf + col0, hnext, STASH ? stash_l + (size_t)col0 * kTileM : nullptr);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int c0 = col0 + c * 16;
@@ -101,7 +101,7 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
     if (c + 1 < 4) {
       ptx::tmem_wait_ld();
       tc_sines16<REDUCE, STASH>(v[(c + 1) & 1], sbuf + c0 + 16, hnext,
-                                 (STASH && stash_l) ? stash_l + c0 + 16 : nullptr);
+                                 STASH ? stash_l + (size_t)(c0 + 16) * kTileM : nullptr);
       if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(lane_base + c0 + 32, v[c & 1]);
     }
     if (!LAST) {
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         for (int j = 0; j < 4; ++j)
           if (j < cin) x[j] = cp[j];
       }
-      __half* st_row = (STASH && valid) ? stash + (t * P + p) * SH : nullptr;  // cos stash of this (frame, point)
+      __half* st_row = STASH ? stash + (size_t)tile * SH * kTileM + row * 8 : nullptr;  // see tc_common.cuh
       if (tracer) CNF_TRACE_EVENT(trole, 100);  // tile start
       ptx::bar_sync(bar_wg, 128);           // everyone is done with the previous tile's shift buffers
       if (wq < 2) tail->shift_s[g][0][col0 + row] = __ldg(sh + col0 + row);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
             float c16[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) c16[j] = cs0[q * 16 + j];
-            tc_stash16(st_row ? st_row + c0 + q * 16 : nullptr, c16);  // every lane calls it (it ends in __syncwarp)
+            tc_stash16(st_row + (size_t)(c0 + q * 16) * kTileM, c16);
           }
         }
       }
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       for (int l = 1; l < nl; ++l) {
         const float* sbuf = layer_prologue(l);
         tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, col0, sbuf, tail->w_out_s, cout, y,
-                                                     st_row ? st_row + (size_t)l * H : nullptr);
+                                                     STASH ? st_row + (size_t)l * H * kTileM : nullptr);
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tail->a_full[g]);
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       {
         const float* sbuf = layer_prologue(nl);
         tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, col0, sbuf, tail->w_out_s, cout, y,
-                                                    st_row ? st_row + (size_t)nl * H : nullptr);
+                                                    STASH ? st_row + (size_t)nl * H * kTileM : nullptr);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + nl);
       }
       // ---- head: combine the two column halves, 12-byte store per point
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
       const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
       const bool valid = p < P;
       float* gs = gshift + t * SH;
-      const __half* st_row = stash + (t * P + (valid ? p : 0)) * SH;
+      const __half* st_row = stash + (size_t)tile * SH * kTileM + row * 8;  // tile-major stash, see tc_common.cuh
       float gy[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
 #pragma unroll
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
 #pragma unroll 1
       for (int c0 = col0; c0 < col0 + 64; c0 += 16) {
         float cs[16], dl[16];
-        tc_load_cos16(st_row + (size_t)nl * H + c0, cs);
+        tc_load_cos16(st_row + ((size_t)nl * H + c0) * kTileM, cs);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float gsum = 0.f;
@@ -484,16 +484,23 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
 
 #pragma unroll 1
       for (int l = nl; l >= 1; --l) {
+        // the stashed cos of the layer below does not depend on the MMA: fetch this thread's 64 columns (8 chunks of
+        // 16 bytes, each warp access 512 contiguous bytes) BEFORE waiting for the accumulator, so the latency is hidden
+        uint4 cpk[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          tc_load_cos_chunk(st_row + ((size_t)(l - 1) * H + col0 + q * 8) * kTileM, cpk[q]);
         if (hf == 0 && wq == 0) ptx::mbar_wait(&tail->d_full[g], d_phase);
         d_phase ^= 1u;
         ptx::bar_sync(bar_slot, 256);
         ptx::tc_fence_after();
-#pragma unroll 1
-        for (int c0 = col0; c0 < col0 + 64; c0 += 16) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = col0 + c * 16;
           uint32_t v[16];
           ptx::tmem_ld_32x32b_x16(lane_base + c0, v);
           float cs[16], dl[16];
-          tc_load_cos16(st_row + (size_t)(l - 1) * H + c0, cs);
+          tc_unpack_cos16(cpk[2 * c], cpk[2 * c + 1], cs);
           ptx::tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];

@@ -27,17 +27,21 @@ __device__ __forceinline__ void trace_event(int role, int& n, unsigned long long
 #define CNF_TRACE_EVENT(role, code)
 #endif
 
-// 16 fp16 cosines of this thread's row -> 32 contiguous bytes of the backward stash (nullptr: row out of range)
+// Backward stash (tensor-core precisions): fp16 cos of every sine argument, tile-major so that a warp's accesses are
+// contiguous: element (tile, layer l, column n, row r) lives at
+//     stash[ ((tile*(nl+1) + l)*H + n) / 8 ][ r ][ n % 8 ]      (16-byte chunk of 8 columns per row, 128 rows per chunk)
+// i.e. with st_row = stash + tile*(nl+1)*H*128 + r*8, the chunk of columns [c, c+8) of layer l is st_row + (l*H + c)*128.
+// Thirty-two rows x 16 bytes = 512 contiguous bytes per warp access (4 full lines instead of 32 partial ones), and rows
+// past P have their own (padded) slots, so no lane ever skips an access.
+constexpr int kStashChunkStride = 8 * kTileM;  // halfs between consecutive 8-column chunks of one row
+
+// 16 fp16 cosines (columns c..c+15 of this thread's row) -> two 16-byte chunks; dst = st_row + (l*H + c)*128
 __device__ __forceinline__ void tc_stash16(__half* dst, const float (&c)[16]) {
   uint32_t w[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) w[e] = ptx::pack_f16x2(c[2 * e], c[2 * e + 1]);
-  if (dst != nullptr) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
-  }
-  __syncwarp();  // rows past P skip the store: reconverge before the next warp-aligned tcgen05 instruction
+  *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(dst + kStashChunkStride) = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 template <bool REDUCE, bool STASH>
@@ -56,7 +60,7 @@ __device__ __forceinline__ void tc_sines16(const uint32_t (&v)[16], const float*
       if (STASH) cs[q * 4 + e] = ptx::cos_approx(r);
     }
   }
-  if (STASH) tc_stash16(stash_dst, cs);
+  if (STASH) tc_stash16(stash_dst, cs);  // stash_dst = st_row + (l*H + c)*128, always a valid slot
 }
 
 #ifdef CNF_TRACE
@@ -88,13 +92,11 @@ __device__ __forceinline__ void tc_colsum16_to_global(float (&v)[16], int lane, 
   if ((lane & 1) == 0) atomicAdd(dst + (lane >> 1), v[0]);
 }
 
-// `src` is always a readable row: rows past P read the frame's row 0 (their delta is exactly zero anyway, because
-// their dL/dy is zero and every row of the chain only depends on itself), so the warp never diverges here.
+// 16 stashed cosines of this thread's row (columns c..c+15): src = st_row + (l*H + c)*128
 __device__ __forceinline__ void tc_load_cos16(const __half* src, float (&c)[16]) {
-  const uint4* s4 = reinterpret_cast<const uint4*>(src);
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    const uint4 w = __ldg(s4 + q);
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(src + q * kStashChunkStride));
     const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -105,5 +107,18 @@ __device__ __forceinline__ void tc_load_cos16(const __half* src, float (&c)[16])
   }
 }
 
+// Raw (still packed) variant for prefetching a whole column range before the accumulator is ready.
+__device__ __forceinline__ void tc_load_cos_chunk(const __half* src, uint4& w) {
+  w = __ldg(reinterpret_cast<const uint4*>(src));
+}
+__device__ __forceinline__ void tc_unpack_cos16(const uint4& w0, const uint4& w1, float (&c)[16]) {
+  const uint32_t ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ws[e]));
+    c[2 * e] = f.x;
+    c[2 * e + 1] = f.y;
+  }
+}
 
 }  // namespace cnf

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         for (int j = 0; j < 4; ++j)
           if (j < cin) x[j] = cp[j];
       }
-      __half* st_row = (STASH && valid) ? stash + (t * P + p) * SH : nullptr;
+      __half* st_row = STASH ? stash + (size_t)tile * SH * kTileM + row * 8 : nullptr;  // tile-major stash
 
       // ---- layer 0: K = cin on CUDA cores, always range-reduced (|arg| reaches tens of radians)
 #pragma unroll 1
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
           if (STASH) cs[j] = ptx::cos_approx(r);
         }
         tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
-        if (STASH) tc_stash16(st_row ? st_row + c0 : nullptr, cs);
+        if (STASH) tc_stash16(st_row + (size_t)c0 * kTileM, cs);
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
           ptx::tmem_ld_32x32b_x16(tmem_row + c0, v);
           ptx::tmem_wait_ld();
           float h[16];
-          tc_sines16<REDUCE, STASH>(v, shl + c0, h, st_row ? st_row + (size_t)l * H + c0 : nullptr);
+          tc_sines16<REDUCE, STASH>(v, shl + c0, h, STASH ? st_row + ((size_t)l * H + c0) * kTileM : nullptr);
           if (!last) {
             tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
           } else {
@@ -414,8 +414,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
       const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
       const bool valid = p < P;
       float* gs = gshift + t * SH;
-      // rows past P read the frame's row 0: their delta is exactly zero (their dL/dy is), and the warp stays converged
-      const __half* st_row = stash + (t * P + (valid ? p : 0)) * SH;
+      const __half* st_row = stash + (size_t)tile * SH * kTileM + row * 8;  // tile-major stash, see tc_common.cuh
       float gy[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
 #pragma unroll
@@ -426,7 +425,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
 #pragma unroll 1
       for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
         float cs[16], dl[16];
-        tc_load_cos16(st_row + (size_t)nl * H + c0, cs);
+        tc_load_cos16(st_row + ((size_t)nl * H + c0) * kTileM, cs);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float g = 0.f;
@@ -445,13 +444,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
 
 #pragma unroll 1
       for (int l = nl; l >= 1; --l) {
+        // prefetch this thread's stashed cos of the layer below (independent of the MMA) before waiting for it
+        constexpr int kChunks = C::kColsPerGroup / 8;
+        uint4 cpk[kChunks];
+#pragma unroll
+        for (int q = 0; q < kChunks; ++q)
+          tc_load_cos_chunk(st_row + ((size_t)(l - 1) * H + col_lo + q * 8) * kTileM, cpk[q]);
         tc_wait_d_full(tail, warp, d_phase);
-#pragma unroll 1
-        for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
+#pragma unroll
+        for (int c = 0; c < kChunks / 2; ++c) {
+          const int c0 = col_lo + c * 16;
           uint32_t v[16];
           ptx::tmem_ld_32x32b_x16(tmem_row + c0, v);
           float cs[16], dl[16];
-          tc_load_cos16(st_row + (size_t)(l - 1) * H + c0, cs);
+          tc_unpack_cos16(cpk[2 * c], cpk[2 * c + 1], cs);
           ptx::tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
