@@ -42,6 +42,13 @@ def load() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = lib_path()
+    if not os.path.exists(path) and "CONFILD_CNF_LIB" not in os.environ:
+        try:  # the library is a build artefact (git-ignored): compile it on first use when nvcc is around
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(
+                f"{path} not found and building it failed ({e}); build it with `python -m confild_b200.build` "
+                "(there is no CPU or PyTorch fallback for the CNF decode path)") from e
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} not found: build it with `python -m confild_b200.build` "

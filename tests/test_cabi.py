@@ -32,7 +32,7 @@ def test_sizes_and_argument_checks(lib):
     assert _native.packed_bytes(d) > 4 * 346115
     assert _native.tc_supported(d)
     assert not _native.tc_supported(_native.dims(2, 32, 64, 2, 3))
-    assert _native.stash_bytes(d, _native.PREC_BF16X3, 4, 100) == 4 * 100 * 11 * 128 * 2
+    assert _native.stash_bytes(d, _native.PREC_BF16X3, 4, 100) == 4 * 128 * 11 * 128 * 2  # rows padded to whole tiles
     assert _native.stash_bytes(d, _native.PREC_FP32, 4, 100) == 4 * 100 * 11 * 128 * 4
     n = ctypes.c_size_t(0)
     bad = _native.dims(0, 128, 128, 10, 3)

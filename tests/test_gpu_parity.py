@@ -33,6 +33,50 @@ def precisions_for(dims):
     return ["fp32", "bf16x3", "fp16"] if _native.tc_supported(d) else ["fp32"]
 
 
+def test_raw_c_abi_forward_backward():
+    """The C ABI called directly with raw device pointers (no nn.Module in between): pack, FiLM shift, forward with
+    stash, backward, FiLM-shift backward -- what INTEGRATION.md shows a maintainer."""
+    import ctypes
+
+    lib = _native.load()
+    dims = O.CASE_SHAPES["case1"]
+    cin, L, cout, nl, H = dims
+    sd = O.init_params(*dims, seed=0)
+    T, P = 3, 200
+    coords, lat = O.synthetic_inputs(cin, L, T, P)
+    gout = torch.randn(T, P, cout, generator=torch.Generator().manual_seed(7))
+    d = _native.dims(cin, L, H, nl, cout)
+    flat = torch.cat([v.reshape(-1) for v in sd.values()]).cuda()
+    assert flat.numel() == _native.param_count(d)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    packed = torch.empty(_native.packed_bytes(d), dtype=torch.uint8, device="cuda")
+    assert lib.cnf_pack_weights(d, vp(flat), ctypes.c_float(30.0), vp(packed), packed.numel(), stream) == 0
+    c_d, l_d, g_d = coords.cuda(), lat.cuda(), gout.cuda()
+    shift = torch.empty(T, (nl + 1) * H, device="cuda")
+    out = torch.empty(T, P, cout, device="cuda")
+    assert lib.cnf_film_shift(d, vp(packed), vp(l_d), T, vp(shift), stream) == 0
+    # FiLM shift against its definition: w0 * (b_l + V_l z_t)
+    want_shift = torch.cat([30.0 * (sd[f"net1.{i}.bias"] + lat @ sd[f"net2.{i}.weight"].T) for i in range(nl + 1)], dim=1)
+    assert O.rel_l2(shift, want_shift) < 1e-6
+    for prec in (_native.PREC_BF16X3, _native.PREC_FP32):
+        nst = _native.stash_bytes(d, prec, T, P)
+        stash = torch.empty(nst, dtype=torch.uint8, device="cuda")
+        assert lib.cnf_forward(d, vp(packed), prec, vp(c_d), 0, vp(shift), vp(out), T, P, vp(stash), nst, stream) == 0
+        gshift = torch.empty(T, (nl + 1) * H, device="cuda")
+        glat = torch.empty(T, L, device="cuda")
+        assert lib.cnf_backward(d, vp(packed), prec, vp(g_d), vp(stash), nst, vp(gshift), T, P, stream) == 0
+        assert lib.cnf_film_shift_backward(d, vp(packed), vp(gshift), T, vp(glat), stream) == 0
+        torch.cuda.synchronize()
+        assert O.rel_l2(out, O.forward(sd, coords[None], lat[:, None])) <= 1e-4
+        assert O.rel_l2(glat, O.grad_latents_from_gout(sd, coords[None], lat[:, None], gout).reshape(T, L)) <= 1e-2
+    # error paths: too-small stash, unsupported precision/shape combination
+    assert lib.cnf_forward(d, vp(packed), 1, vp(c_d), 0, vp(shift), vp(out), T, P, vp(stash), 16, stream) == 4
+    assert b"stash" in lib.cnf_last_error()
+    d_odd = _native.dims(2, 32, 64, 2, 3)
+    assert lib.cnf_forward(d_odd, vp(packed), 1, vp(c_d), 0, vp(shift), vp(out), T, P, None, 0, stream) == 2
+
+
 def test_library_loaded_and_device_is_blackwell():
     _native.load()
     assert torch.cuda.get_device_capability(0)[0] == 10
@@ -190,6 +234,25 @@ def test_repack_on_weight_change_and_w0():
         assert O.rel_l2(y2, O.forward(sd2, coords[None], lat[:, None], w0=20.0)) < 1e-4
     finally:
         m.nl.w0 = 30.0
+
+
+@pytest.mark.parametrize("case,T,P", [("case4", 6, 131072), ("case2", 8, 65536)])
+def test_large_generic_kernel_vs_fp32_chain(case, T, P):
+    """H=256/384 tensor-core kernels at a BASELINE config-3 sized point set against the fp32 CUDA-core chain
+    (every frame) and against the CPU oracle on a strided subset of points."""
+    dims = O.CASE_SHAPES[case]
+    sd = O.init_params(*dims, seed=0)
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    c, l = coords.cuda()[None], lat.cuda()[:, None]
+    with torch.no_grad():
+        y = make_model(dims, sd, "bf16x3")(c, l)
+        y32 = make_model(dims, sd, "fp32")(c, l)
+    err = O.rel_l2(y, y32)
+    print(f"{case} T={T} P={P}: bf16x3 vs fp32 chain {err:.3e}")
+    assert err <= 1e-4
+    pts = torch.arange(5, P, 1021)
+    want = O.forward(sd, coords[None, pts], lat[:, None])
+    assert O.rel_l2(y[:, pts.cuda()], want) <= 1e-4
 
 
 def test_full_size_properties_config2():
