@@ -273,12 +273,25 @@ def main_ours(args):
     coords_h, lat_h = coords_h.pin_memory(), lat_h.pin_memory()
     coords, lat = coords_h.to(dev)[None], lat_h.to(dev)[:, None]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world * T, P, cout), dtype=torch.float32, device=dev) if world > 1 else None
     kernel_events = []
     model._timing = kernel_events
+    gather_mode = "none"
+    fused = gathered = None
+    if world > 1:
+        try:  # all-gather fused into the decode kernel (peer stores over NVLink from the epilogue)
+            if args.gather == "nccl":
+                raise RuntimeError("NCCL all-gather requested")
+            fused = cb.FusedGatherDecoder(model, T, P)
+            gather_mode = "fused into the decode kernel: epilogue stores to all ranks' symmetric-memory buffers over NVLink"
+        except Exception as e:  # noqa: BLE001 - symmetric memory unavailable: decode + NCCL all_gather_into_tensor
+            fused = None
+            gathered = torch.empty((world * T, P, cout), dtype=torch.float32, device=dev)
+            gather_mode = f"decode + NCCL all_gather_into_tensor ({type(e).__name__}: {e})"[:200]
 
     def step():
         with torch.no_grad():
+            if fused is not None:
+                return fused(coords, lat)
             y = model(coords, lat)
             if world > 1:
                 dist.all_gather_into_tensor(gathered, y)
@@ -357,7 +370,7 @@ def main_ours(args):
                        "precision": {"bf16x3": "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate",
                                      "fp16": "tcgen05 single fp16 MMA per product, fp32 accumulate",
                                      "fp32": "CUDA-core fp32 FMA"}[args.precision],
-                       "parallelism": f"frames sharded over {world} GPU(s)" + ("; NCCL all-gather of the field inside the step" if world > 1 else ""),
+                       "parallelism": f"frames sharded over {world} GPU(s)" + (f"; all-gather of the field inside the step, {gather_mode}" if world > 1 else ""),
                        "l2": "256 MiB memset between timed steps; each step also writes %.0f MB of output" % (T * P * cout * 4 / 1e6)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(coords_h.numel() * 4 + lat_h.numel() * 4),
@@ -396,6 +409,7 @@ def main():
     ap.add_argument("--points", type=int, default=POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the fast-mode and DPS side measurements")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N>1: how the decoded field is all-gathered")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)

@@ -19,7 +19,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
 #: every symbol include/confild_cnf.h declares (checked by tests/test_cabi.py)
 EXPORTS = [
     "cnf_abi_version", "cnf_last_error", "cnf_tc_supported", "cnf_param_count", "cnf_packed_bytes",
-    "cnf_pack_weights", "cnf_film_shift", "cnf_stash_bytes", "cnf_forward", "cnf_backward",
+    "cnf_pack_weights", "cnf_film_shift", "cnf_stash_bytes", "cnf_forward", "cnf_forward_gather", "cnf_backward",
     "cnf_film_shift_backward", "cnf_query_launch",
 ]
 
@@ -74,6 +74,8 @@ def load() -> ctypes.CDLL:
     lib.cnf_stash_bytes.argtypes = [dp, i32, i64, i64, ctypes.POINTER(sz)]
     lib.cnf_forward.restype = i32
     lib.cnf_forward.argtypes = [dp, vp, i32, vp, i64, vp, vp, i64, i64, vp, sz, vp]
+    lib.cnf_forward_gather.restype = i32
+    lib.cnf_forward_gather.argtypes = [dp, vp, i32, vp, i64, vp, ctypes.POINTER(vp), i32, i64, i64, vp]
     lib.cnf_backward.restype = i32
     lib.cnf_backward.argtypes = [dp, vp, i32, vp, vp, sz, vp, i64, i64, vp]
     lib.cnf_film_shift_backward.restype = i32

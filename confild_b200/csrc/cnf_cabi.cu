@@ -97,7 +97,7 @@ int make_tc_plan(const DeviceInfo& di, int64_t tiles, TcPlan* plan) {
 
 template <int H, int PREC, bool STASH, bool REDUCE>
 int launch_tc_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs, const float* shift,
-                      float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
+                      cnf::OutTargets out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
@@ -113,7 +113,7 @@ int launch_tc_forward(const cnf_dims& d, const uint8_t* packed, const float* coo
 
 template <int H, int PREC>
 int dispatch_tc_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs,
-                        const float* shift, float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
+                        const float* shift, cnf::OutTargets out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
   const bool reduce = env_int("CNF_TC_REDUCE", 0) != 0;
   if (stash) {
     return reduce ? launch_tc_forward<H, PREC, true, true>(d, packed, coords, cfs, shift, out, stash, T, P, st)
@@ -125,7 +125,7 @@ int dispatch_tc_forward(const cnf_dims& d, const uint8_t* packed, const float* c
 
 template <int PREC>
 int dispatch_tc_forward_h(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs,
-                          const float* shift, float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
+                          const float* shift, cnf::OutTargets out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
   switch (d.H) {
     case 128: return dispatch_tc_forward<128, PREC>(d, packed, coords, cfs, shift, out, stash, T, P, st);
     case 256: return dispatch_tc_forward<256, PREC>(d, packed, coords, cfs, shift, out, stash, T, P, st);
@@ -155,7 +155,7 @@ int make_tc2_plan(const DeviceInfo& di, int64_t tiles, TcPlan* plan) {
 
 template <int PREC, bool REDUCE, bool STASH>
 int launch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs, const float* shift,
-                       float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
+                       cnf::OutTargets out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
@@ -171,7 +171,7 @@ int launch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* co
 
 template <int PREC>
 int dispatch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs,
-                         const float* shift, float* out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
+                         const float* shift, cnf::OutTargets out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
   const bool reduce = env_int("CNF_TC_REDUCE", 0) != 0;
   if (stash)
     return reduce ? launch_tc2_forward<PREC, true, true>(d, packed, coords, cfs, shift, out, stash, T, P, st)
@@ -318,9 +318,10 @@ int cnf_stash_bytes(const cnf_dims* dims, int precision, int64_t T, int64_t P, s
   return CNF_OK;
 }
 
-int cnf_forward(const cnf_dims* dims, const void* d_packed, int precision, const float* d_coords,
-                int64_t coord_frame_stride, const float* d_shift, float* d_out, int64_t T, int64_t P, void* d_stash,
-                size_t stash_bytes, void* stream) {
+static int forward_impl(const cnf_dims* dims, const void* d_packed, int precision, const float* d_coords,
+                        int64_t coord_frame_stride, const float* d_shift, cnf::OutTargets outs, int64_t T, int64_t P,
+                        void* d_stash, size_t stash_bytes, void* stream) {
+  float* d_out = outs.ptr[0];
   if (int rc = check_dims(dims)) return rc;
   if (!d_packed || !d_coords || !d_shift || !d_out) return fail(CNF_ERR_INVALID_ARGUMENT, "NULL device pointer");
   if (T < 1 || P < 1) return fail(CNF_ERR_INVALID_ARGUMENT, "T=%lld P=%lld", (long long)T, (long long)P);
@@ -333,6 +334,7 @@ int cnf_forward(const cnf_dims* dims, const void* d_packed, int precision, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint8_t* packed = static_cast<const uint8_t*>(d_packed);
   if (precision == CNF_PREC_FP32) {
+    if (outs.n != 1) return fail(CNF_ERR_UNSUPPORTED, "the fused gather needs a tensor-core precision");
     DeviceInfo di;
     if (int rc = device_info(&di)) return rc;
     const size_t smem = simt_smem_bytes(*dims);
@@ -361,16 +363,41 @@ int cnf_forward(const cnf_dims* dims, const void* d_packed, int precision, const
                 dims->H, dims->nl, dims->cin, dims->cout);
   if (use_tc2(*dims)) {
     return precision == CNF_PREC_BF16X3
-               ? dispatch_tc2_forward<CNF_PREC_BF16X3>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out,
+               ? dispatch_tc2_forward<CNF_PREC_BF16X3>(*dims, packed, d_coords, coord_frame_stride, d_shift, outs,
                                                        d_stash, T, P, st)
-               : dispatch_tc2_forward<CNF_PREC_FP16>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out,
+               : dispatch_tc2_forward<CNF_PREC_FP16>(*dims, packed, d_coords, coord_frame_stride, d_shift, outs,
                                                      d_stash, T, P, st);
   }
   if (precision == CNF_PREC_BF16X3)
-    return dispatch_tc_forward_h<CNF_PREC_BF16X3>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out, d_stash,
+    return dispatch_tc_forward_h<CNF_PREC_BF16X3>(*dims, packed, d_coords, coord_frame_stride, d_shift, outs, d_stash,
                                                   T, P, st);
-  return dispatch_tc_forward_h<CNF_PREC_FP16>(*dims, packed, d_coords, coord_frame_stride, d_shift, d_out, d_stash, T,
+  return dispatch_tc_forward_h<CNF_PREC_FP16>(*dims, packed, d_coords, coord_frame_stride, d_shift, outs, d_stash, T,
                                               P, st);
+}
+
+int cnf_forward(const cnf_dims* dims, const void* d_packed, int precision, const float* d_coords,
+                int64_t coord_frame_stride, const float* d_shift, float* d_out, int64_t T, int64_t P, void* d_stash,
+                size_t stash_bytes, void* stream) {
+  cnf::OutTargets outs{};
+  outs.ptr[0] = d_out;
+  outs.n = 1;
+  return forward_impl(dims, d_packed, precision, d_coords, coord_frame_stride, d_shift, outs, T, P, d_stash,
+                      stash_bytes, stream);
+}
+
+int cnf_forward_gather(const cnf_dims* dims, const void* d_packed, int precision, const float* d_coords,
+                       int64_t coord_frame_stride, const float* d_shift, float* const* d_outs, int n_out, int64_t T,
+                       int64_t P, void* stream) {
+  if (!d_outs) return fail(CNF_ERR_INVALID_ARGUMENT, "d_outs is NULL");
+  if (n_out < 1 || n_out > cnf::kMaxOutTargets)
+    return fail(CNF_ERR_INVALID_ARGUMENT, "n_out=%d, must be in [1,%d]", n_out, cnf::kMaxOutTargets);
+  cnf::OutTargets outs{};
+  for (int k = 0; k < n_out; ++k) {
+    if (!d_outs[k]) return fail(CNF_ERR_INVALID_ARGUMENT, "d_outs[%d] is NULL", k);
+    outs.ptr[k] = d_outs[k];
+  }
+  outs.n = n_out;
+  return forward_impl(dims, d_packed, precision, d_coords, coord_frame_stride, d_shift, outs, T, P, nullptr, 0, stream);
 }
 
 int cnf_backward(const cnf_dims* dims, const void* d_packed, int precision, const float* d_gout, const void* d_stash,

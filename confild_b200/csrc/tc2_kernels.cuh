@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
                                                                      const float* __restrict__ coords,
                                                                      int64_t coord_frame_stride,
                                                                      const float* __restrict__ shift,
-                                                                     float* __restrict__ out, __half* __restrict__ stash,
+                                                                     OutTargets outs, __half* __restrict__ stash,
                                                                      int64_t T, int64_t P, int num_stages) {
   constexpr int H = kTc2H;
   constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
@@ -280,11 +280,16 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       ptx::bar_sync(bar_slot, 256);
       if (hf == 0 && valid) {
         const float4 yp = *reinterpret_cast<const float4*>(tail->y_part[g][row]);
-        const float ys[4] = {y[0] + yp.x, y[1] + yp.y, y[2] + yp.z, y[3] + yp.w};
-        float* op = out + (t * P + p) * cout;
+        float ys[4] = {y[0] + yp.x, y[1] + yp.y, y[2] + yp.z, y[3] + yp.w};
 #pragma unroll
         for (int o = 0; o < 4; ++o)
-          if (o < cout) op[o] = ys[o] + __ldg(b_out + o);
+          if (o < cout) ys[o] += __ldg(b_out + o);
+        for (int k = 0; k < outs.n; ++k) {  // one target, or every rank's gathered buffer (peer stores over NVLink)
+          float* op = outs.ptr[k] + (t * P + p) * cout;
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < cout) op[o] = ys[o];
+        }
       }
       __syncwarp();  // rows past P skipped the store: reconverge before the next tile's warp-aligned instructions
     }

@@ -10,6 +10,15 @@ namespace cnf {
 
 constexpr int kTcMaxStages = 12;
 
+// Where the decoded field goes: this rank's (T, P, cout) block inside up to 8 output buffers.  n == 1 is the plain
+// case; n > 1 is the fused all-gather: the other pointers are the peers' buffers mapped over NVLink (each already
+// offset to this rank's frame range), written with ordinary stores from the epilogue, so the gather costs no extra pass.
+constexpr int kMaxOutTargets = 8;
+struct OutTargets {
+  float* ptr[kMaxOutTargets];
+  int n;
+};
+
 #ifdef CNF_TRACE
 // Debug build only: per-role event trace of CTA 0 (role r writes (code, clock64) pairs at trace[r*8192 + 2*n]).
 __device__ unsigned long long* g_trace = nullptr;

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
                                                                    const float* __restrict__ coords,
                                                                    int64_t coord_frame_stride,
                                                                    const float* __restrict__ shift,
-                                                                   float* __restrict__ out, __half* __restrict__ stash,
+                                                                   OutTargets outs, __half* __restrict__ stash,
                                                                    int64_t T, int64_t P, int num_stages) {
   using C = TcCfg<H, PREC>;
   extern __shared__ uint8_t smem_raw[];
@@ -326,10 +326,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
           const float4 yp = y_part[k * kTileM + row];
           ys[0] += yp.x; ys[1] += yp.y; ys[2] += yp.z; ys[3] += yp.w;
         }
-        float* op = out + (t * P + p) * cout;
 #pragma unroll
         for (int o = 0; o < 4; ++o)
-          if (o < cout) op[o] = ys[o] + __ldg(b_out + o);
+          if (o < cout) ys[o] += __ldg(b_out + o);
+        for (int k = 0; k < outs.n; ++k) {  // one target, or every rank's gathered buffer (peer stores over NVLink)
+          float* op = outs.ptr[k] + (t * P + p) * cout;
+#pragma unroll
+          for (int o = 0; o < 4; ++o)
+            if (o < cout) op[o] = ys[o];
+        }
       }
       __syncwarp();
       ptx::bar_sync(1, kTcEpiWarps * 32);  // partial sums consumed before the next tile's layer 0 overwrites them

@@ -88,3 +88,38 @@ def decode_frame_sharded(decode_fn: Callable[[torch.Tensor], torch.Tensor], late
         w.wait()
     # (chunk, rank, frame) -> (rank, chunk, frame) = global frame order
     return full.permute(1, 0, 2, *range(3, full.dim())).reshape((T,) + tuple(full.shape[3:]))
+
+
+class FusedGatherDecoder:
+    """Frame-sharded decode whose all-gather is fused into the decode kernel (GPUs of one NVLink/NVSwitch box).
+
+    Every rank allocates the gathered field ``(world*T_local, P, cout)`` in torch symmetric memory and maps its peers'
+    buffers; ``__call__`` then runs ``cnf_forward_gather``: the kernel's epilogue stores each decoded point straight
+    into all ``world`` buffers (12 bytes per point and target over NVLink), so there is no separate collective pass --
+    only a barrier.  Equal shards only (``T_local`` frames per rank).  The returned tensor is the rank's symmetric
+    buffer: consume (or copy) it before the next call, which overwrites it on every rank.
+    """
+
+    def __init__(self, model, T_local: int, P: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if not dist.is_initialized():
+            raise RuntimeError("FusedGatherDecoder needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("the fused gather supports up to 8 ranks (one NVSwitch box)")
+        self.model, self.T_local, self.P = model, int(T_local), int(P)
+        cout = int(model.net1[-1].weight.shape[0])
+        dev = model.net1[0].weight.device
+        self.buf = symm_mem.empty((self.world * self.T_local, self.P, cout), dtype=torch.float32, device=dev)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        block_bytes = self.T_local * self.P * cout * 4
+        # every rank's buffer, offset to THIS rank's frame range
+        self.out_ptrs = [int(p) + self.rank * block_bytes for p in self.handle.buffer_ptrs]
+
+    def __call__(self, coords: torch.Tensor, latents_local: torch.Tensor) -> torch.Tensor:
+        self.model.decode_into(coords, latents_local, self.out_ptrs, T_expected=self.T_local)
+        self.handle.barrier()  # all ranks' stores have landed (stream-ordered device barrier over the signal pads)
+        return self.buf

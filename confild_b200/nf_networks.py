@@ -285,6 +285,40 @@ class SIRENAutodecoder_film(nn.Module):
                 timing.append((e0, e1))
         return out, stash
 
+    @torch.no_grad()
+    def decode_into(self, coords, latents, out_ptrs, T_expected: Optional[int] = None) -> Tuple[int, int]:
+        """Decode and store this call's ``(T, P, cout)`` block at every device address in ``out_ptrs`` (the fused
+        all-gather: the caller passes its own gathered buffer and the peers' NVLink-mapped buffers, each offset to
+        this rank's frame range; see ``distributed.FusedGatherDecoder``).  No autograd.  Returns ``(T, P)``."""
+        import ctypes
+
+        lib = _native.load()
+        d = self._cdims()
+        cin, L, H, nl, cout = self._dims_tuple
+        coords_c, stride, lat2d, T, P, _ = canonicalize(coords, latents)
+        if T_expected is not None and T != T_expected:
+            raise ValueError(f"expected {T_expected} frames, got {T}")
+        prec = self._precision_code()
+        dev = lat2d.device
+        packed = self._ensure_packed()
+        shift = torch.empty((T, (nl + 1) * H), dtype=torch.float32, device=dev)
+        ptrs = (ctypes.c_void_p * len(out_ptrs))(*[int(p) for p in out_ptrs])
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _native.check(lib.cnf_film_shift(d, packed.data_ptr(), lat2d.data_ptr(), T, shift.data_ptr(), stream),
+                          "cnf_film_shift")
+            timing = getattr(self, "_timing", None)
+            if timing is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            _native.check(lib.cnf_forward_gather(d, packed.data_ptr(), prec, coords_c.data_ptr(), stride,
+                                                 shift.data_ptr(), ptrs, len(out_ptrs), T, P, stream),
+                          "cnf_forward_gather")
+            if timing is not None:
+                e1.record()
+                timing.append((e0, e1))
+        return T, P
+
     def _launch_backward(self, gout, stash, packed, prec, T, P) -> torch.Tensor:
         lib = _native.load()
         d = self._cdims()

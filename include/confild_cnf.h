@@ -103,6 +103,17 @@ int cnf_forward(const cnf_dims* dims, const void* d_packed, int precision, const
                 int64_t coord_frame_stride, const float* d_shift, float* d_out, int64_t T, int64_t P,
                 void* d_stash, size_t stash_bytes, void* stream);
 
+/* Decode with the all-gather fused into the kernel: this rank's (T,P,cout) block is stored into n_out buffers, the
+ * pointers in the HOST array d_outs (1 <= n_out <= 8): its own gathered buffer and the peers' buffers mapped into this
+ * process over NVLink (CUDA IPC / torch symmetric memory), each already offset to this rank's frame range.  The epilogue
+ * writes 4*cout bytes per point to every target, so the gather costs no extra pass over the field; the caller
+ * synchronises the ranks afterwards.  Tensor-core precisions only, no stash.
+ * Replaces: decode followed by the one collective of the path, all_gather_into_tensor of the decoded field
+ * (the reference itself decodes on a single GPU, inference_function.py:51-76). */
+int cnf_forward_gather(const cnf_dims* dims, const void* d_packed, int precision, const float* d_coords,
+                       int64_t coord_frame_stride, const float* d_shift, float* const* d_outs, int n_out, int64_t T,
+                       int64_t P, void* stream);
+
 /* Backward to the FiLM shifts: given d_gout = dLoss/dout (T,P,cout) and the stash of the
  * matching cnf_forward call, accumulates d_gshift[t, l*H+n] = sum_p dLoss/d(arg of sine l,n at t,p).
  * d_gshift (T,(nl+1)*H) is zeroed by this call before accumulation.
