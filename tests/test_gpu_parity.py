@@ -316,6 +316,45 @@ def test_reference_callers_shapes():
     assert host.device.type == "cpu" and O.rel_l2(host, want) < 1e-4
 
 
+def test_folded_normalizers_on_gpu():
+    """f2: normalise / denormalise / latent un-normalise folded into the weights -- no extra element-wise pass."""
+    dims = O.CASE_SHAPES["case1"]
+    sd = O.init_params(*dims, seed=0)
+    m = make_model(dims, sd, "bf16x3")
+    g = torch.Generator().manual_seed(5)
+
+    class N:
+        method = "-11"
+
+        def __init__(self, hi, lo):
+            self.params = (hi, lo)
+
+        def normalize(self, x):
+            hi, lo = (p.to(x.device) for p in self.params)
+            return (x - lo) / (hi - lo) * 2 - 1
+
+        def denormalize(self, y):
+            hi, lo = (p.to(y.device) for p in self.params)
+            return (y + 1) / 2 * (hi - lo) + lo
+
+    xn, yn = N(torch.tensor([2.0, 3.0]), torch.tensor([-1.0, 0.5])), N(torch.tensor([1.0, 2.0, 3.0]), torch.tensor([-1.0, -2.0, 0.0]))
+    zmax, zmin = torch.rand(128, generator=g) * 0.3 + 0.1, -torch.rand(128, generator=g) * 0.3 - 0.1
+    a_z, c_z = (zmax - zmin) / 2, (zmax + zmin) / 2           # measurements.py:219-220: (z+1)(max-min)/2 + min
+    coords = torch.rand(700, 2, generator=g) * torch.tensor([3.0, 2.5]) + torch.tensor([-1.0, 0.5])
+    z = torch.rand(6, 128, generator=g) * 2 - 1
+    want = yn.denormalize(O.forward(sd, xn.normalize(coords)[None], (a_z * z + c_z)[:, None]))
+    folded = cb.fold_normalizers(m, xn, yn, latent_affine=(a_z, c_z))
+    zg = z.cuda()[:, None].requires_grad_(True)
+    y = folded(coords.cuda()[None], zg)
+    assert O.rel_l2(y, want) < 1e-4
+    gout = torch.randn(y.shape, generator=g)
+    (gz,) = torch.autograd.grad(y, zg, grad_outputs=gout.cuda())
+    zc = z[:, None].clone().requires_grad_(True)
+    yc = yn.denormalize(O.forward(sd, xn.normalize(coords)[None], a_z * zc + c_z))
+    (gzc,) = torch.autograd.grad(yc, zc, grad_outputs=gout)
+    assert O.rel_l2(gz, gzc) < 1e-2
+
+
 def test_training_mode_with_grad_raises():
     m = cb.SIRENAutodecoder_film(2, 128, 3, 10, 128).cuda()  # training mode, params require grad
     with pytest.raises(NotImplementedError):

@@ -120,3 +120,39 @@ def test_decode_drivers_equal_reference_loop():
     assert torch.allclose(got, want, atol=1e-6)
     got2 = cb.decoder(coords, lat, model, xn, yn, 4, "cpu")
     assert torch.allclose(got2, want, atol=1e-6) and got2.device.type == "cpu"
+
+
+class _RefNorm:
+    """The reference's Normalizer_ts arithmetic (cnf/utils/normalize.py:100-120) for the folding test."""
+
+    def __init__(self, method, params):
+        self.method, self.params = method, params
+
+    def normalize(self, x):
+        p0, p1 = self.params
+        return {"-11": lambda: (x - p1) / (p0 - p1) * 2 - 1, "01": lambda: (x - p1) / (p0 - p1),
+                "ms": lambda: (x - p0) / p1, "none": lambda: x}[self.method]()
+
+    def denormalize(self, y):
+        p0, p1 = self.params
+        return {"-11": lambda: (y + 1) / 2 * (p0 - p1) + p1, "01": lambda: y * (p0 - p1) + p1,
+                "ms": lambda: y * p1 + p0, "none": lambda: y}[self.method]()
+
+
+@pytest.mark.parametrize("xm,ym", [("-11", "-11"), ("01", "ms"), ("ms", "none"), ("none", "01")])
+def test_fold_normalizers_matches_explicit_affines(xm, ym):
+    """Folded parameters, evaluated by the oracle in fp64, equal normalise -> decode -> denormalise."""
+    torch.manual_seed(0)
+    m = cb.SIRENAutodecoder_film(2, 16, 3, 2, 32).double()
+    g = torch.Generator().manual_seed(4)
+    xn = _RefNorm(xm, (torch.tensor([2.0, 3.5], dtype=torch.float64), torch.tensor([-1.0, 0.5], dtype=torch.float64)))
+    yn = _RefNorm(ym, (torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64), torch.tensor([0.5, 0.25, 2.0], dtype=torch.float64)))
+    a_z = torch.rand(16, generator=g, dtype=torch.float64) + 0.5
+    c_z = torch.randn(16, generator=g, dtype=torch.float64) * 0.1
+    coords = torch.rand(1, 40, 2, generator=g, dtype=torch.float64) * 3 - 1
+    lat = torch.randn(5, 1, 16, generator=g, dtype=torch.float64) * 0.2
+    want = yn.denormalize(O.forward(m.state_dict(), xn.normalize(coords), a_z * lat + c_z))
+    folded = cb.fold_normalizers(m, xn, yn, latent_affine=(a_z, c_z))
+    got = O.forward(folded.state_dict(), coords, lat)
+    assert torch.allclose(got, want, rtol=1e-10, atol=1e-10)
+    assert not torch.equal(folded.net1[0].weight, m.net1[0].weight) or xm == "none"
