@@ -294,9 +294,12 @@ int cnf_film_shift_backward(const cnf_dims* dims, const void* d_packed, const fl
   const cnf::PackedLayout lay = cnf::make_layout(*dims);
   const uint8_t* packed = static_cast<const uint8_t*>(d_packed);
   const int K = (dims->nl + 1) * dims->H;
-  dim3 grid((dims->L + 63) / 64, (unsigned)((T + 63) / 64));
-  cnf::simt_gemm_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_gshift, reinterpret_cast<const float*>(packed + lay.v_cat), nullptr, d_glatents, T, dims->L, K);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CNF_CUDA(cudaMemsetAsync(d_glatents, 0, (size_t)T * dims->L * sizeof(float), st));
+  if (T > 2147483647LL) return fail(CNF_ERR_UNSUPPORTED, "T=%lld exceeds the grid limit", (long long)T);
+  dim3 grid((unsigned)T, (unsigned)((K + cnf::kShiftBwdChunk - 1) / cnf::kShiftBwdChunk));
+  cnf::film_shift_backward_kernel<<<grid, 128, 0, st>>>(d_gshift, reinterpret_cast<const float*>(packed + lay.v_cat),
+                                                       d_glatents, K, dims->L);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;
 }

@@ -64,6 +64,28 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
+// glat[t][j] += sum_{i in this block's K chunk} gshift[t][i] * V[i][j]   (K = (nl+1)*H, V row-major [K][L]).
+// The DPS shapes have few frames (T = 64..384) and a long reduction (K = 1408..6144): a (frame, K-chunk) grid with
+// split-K atomics keeps every SM busy where a 64x64-tile GEMM would run on one or two blocks.  glat is pre-zeroed.
+constexpr int kShiftBwdChunk = 128;
+__global__ void __launch_bounds__(128) film_shift_backward_kernel(const float* __restrict__ gshift,
+                                                                  const float* __restrict__ V, float* __restrict__ glat,
+                                                                  int K, int L) {
+  __shared__ float gs[kShiftBwdChunk];
+  const int64_t t = blockIdx.x;
+  const int i0 = blockIdx.y * kShiftBwdChunk;
+  const int n = min(kShiftBwdChunk, K - i0);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) gs[i] = gshift[t * K + i0 + i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < n; ++i) acc = fmaf(gs[i], __ldg(V + (size_t)(i0 + i) * L + j), acc);
+    atomicAdd(glat + t * L + j, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 constexpr int kSimtTM = 64;  // points per block
 
 // out = A(TMxH, smem) * W(HxH, global, [k][n] layout), one 128-column block at a time.
