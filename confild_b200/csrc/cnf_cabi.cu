@@ -64,6 +64,15 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// Packed tiles (rows = consecutive (frame, point) pairs, a tile may span frames) when frame-aligned 128-point tiles
+// would waste >= 1/6 of their rows on padding: P < 128, or a ragged P of a few hundred.  CNF_TC_PACKED=0/1 forces it.
+int use_packed(int64_t P) {
+  const int forced = env_int("CNF_TC_PACKED", -1);
+  if (forced == 0 || forced == 1) return forced;
+  const int64_t padded = (P + cnf::kTileM - 1) / cnf::kTileM * cnf::kTileM;
+  return padded * 5 >= P * 6 ? 1 : 0;
+}
+
 // Launch plan for a tensor-core kernel: ring depth, shared memory, CTAs per SM, grid.
 struct TcPlan {
   int stages = 0;
@@ -100,13 +109,14 @@ int launch_tc_forward(const cnf_dims& d, const uint8_t* packed, const float* coo
                       cnf::OutTargets out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
-  const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
+  const int pack_rows = use_packed(P);
+  const int64_t tiles = cnf::tc_num_tiles(T, P, pack_rows);
   TcPlan plan;
   if (int rc = make_tc_plan<H, PREC>(di, tiles, &plan)) return rc;
   auto kern = cnf::tc_forward_kernel<H, PREC, STASH, REDUCE>;
   CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   kern<<<(unsigned)plan.grid, cnf::kTcThreads, plan.smem, st>>>(d, packed, coords, cfs, shift, out,
-                                                                reinterpret_cast<__half*>(stash), T, P, plan.stages);
+                                                                reinterpret_cast<__half*>(stash), T, P, plan.stages, pack_rows);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -158,13 +168,14 @@ int launch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* co
                        cnf::OutTargets out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
-  const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
+  const int pack_rows = use_packed(P);
+  const int64_t tiles = cnf::tc_num_tiles(T, P, pack_rows);
   TcPlan plan;
   if (int rc = make_tc2_plan(di, tiles, &plan)) return rc;
   auto kern = cnf::tc2_forward_kernel<PREC, REDUCE, STASH>;
   CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   kern<<<(unsigned)plan.grid, cnf::kTc2Threads, plan.smem, st>>>(d, packed, coords, cfs, shift, out,
-                                                                 reinterpret_cast<__half*>(stash), T, P, plan.stages);
+                                                                 reinterpret_cast<__half*>(stash), T, P, plan.stages, pack_rows);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -184,13 +195,14 @@ int launch_tc2_backward(const cnf_dims& d, const uint8_t* packed, const float* g
                         int64_t T, int64_t P, cudaStream_t st) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
-  const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
+  const int pack_rows = use_packed(P);
+  const int64_t tiles = cnf::tc_num_tiles(T, P, pack_rows);
   TcPlan plan;
   if (int rc = make_tc2_plan(di, tiles, &plan)) return rc;
   auto kern = cnf::tc2_backward_kernel;
   CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   kern<<<(unsigned)plan.grid, cnf::kTc2Threads, plan.smem, st>>>(d, packed, gout, reinterpret_cast<const __half*>(stash),
-                                                                 gshift, T, P, plan.stages);
+                                                                 gshift, T, P, plan.stages, pack_rows);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -200,13 +212,14 @@ int launch_tc_backward(const cnf_dims& d, const uint8_t* packed, const float* go
                        int64_t T, int64_t P, cudaStream_t st) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
-  const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
+  const int pack_rows = use_packed(P);
+  const int64_t tiles = cnf::tc_num_tiles(T, P, pack_rows);
   TcPlan plan;
   if (int rc = make_tc_plan<H, CNF_PREC_BF16X3>(di, tiles, &plan)) return rc;
   auto kern = cnf::tc_backward_kernel<H>;
   CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   kern<<<(unsigned)plan.grid, cnf::kTcThreads, plan.smem, st>>>(d, packed, gout, reinterpret_cast<const __half*>(stash),
-                                                                gshift, T, P, plan.stages);
+                                                                gshift, T, P, plan.stages, pack_rows);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -456,7 +469,7 @@ int cnf_query_launch(const cnf_dims* dims, int precision, int64_t T, int64_t P, 
     v[6] = cnf::kSimtTM;
   } else {
     if (!tc_ok(*dims)) return fail(CNF_ERR_UNSUPPORTED, "tensor-core path unsupported for these dims");
-    const int64_t tiles = T * ((P + cnf::kTileM - 1) / cnf::kTileM);
+    const int64_t tiles = cnf::tc_num_tiles(T, P, use_packed(P));
     TcPlan plan;
     int rc = CNF_ERR_UNSUPPORTED;
     const bool x3 = precision == CNF_PREC_BF16X3;

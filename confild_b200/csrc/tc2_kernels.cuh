@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
                                                                      int64_t coord_frame_stride,
                                                                      const float* __restrict__ shift,
                                                                      OutTargets outs, __half* __restrict__ stash,
-                                                                     int64_t T, int64_t P, int num_stages) {
+                                                                     int64_t T, int64_t P, int num_stages, int pack_rows) {
   constexpr int H = kTc2H;
   constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
   constexpr int kParts = kSplit ? 2 : 1;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
   const int nl = d.nl, cin = d.cin, cout = d.cout;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t PB = (P + kTileM - 1) / kTileM;
-  const int64_t tiles = T * PB;
+  const int64_t tiles = tc_num_tiles(T, P, pack_rows);
   const int64_t pairs = (tiles + 1) / 2;
   const int64_t SH = (int64_t)(nl + 1) * H;
 
@@ -196,9 +196,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + g;
       if (tile >= tiles) continue;
-      const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
-      const bool valid = p < P;
-      const float* sh = shift + t * SH;
+      const RowMap rm = tc_row_map(tile, row, T, P, PB, pack_rows);
+      const int64_t t = rm.t, p = rm.p;
+      const bool valid = rm.valid;
+      const float* sh = shift + t * SH;  // this row's frame (one frame per tile unless the tiles are packed)
       float x[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
         const float* cp = coords + t * coord_frame_stride + p * cin;
@@ -208,9 +209,14 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       }
       __half* st_row = STASH ? stash + (size_t)tile * SH * kTileM + row * 8 : nullptr;  // see tc_common.cuh
       if (tracer) CNF_TRACE_EVENT(trole, 100);  // tile start
-      ptx::bar_sync(bar_wg, 128);           // everyone is done with the previous tile's shift buffers
-      if (wq < 2) tail->shift_s[g][0][col0 + row] = __ldg(sh + col0 + row);
-      ptx::bar_sync(bar_wg, 128);
+      // FiLM shifts: staged per layer in shared memory (one frame per tile), or read per row from global (packed tiles)
+      const float* s0 = sh;
+      if (!pack_rows) {
+        ptx::bar_sync(bar_wg, 128);  // everyone is done with the previous tile's shift buffers
+        if (wq < 2) tail->shift_s[g][0][col0 + row] = __ldg(sh + col0 + row);
+        ptx::bar_sync(bar_wg, 128);
+        s0 = tail->shift_s[g][0];
+      }
 
       // ---- layer 0 on CUDA cores (K = cin), always range-reduced
 #pragma unroll 1
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         [[maybe_unused]] float cs0[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float z = tail->shift_s[g][0][c0 + j];
+          float z = s0[c0 + j];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (i < cin) z = fmaf(tail->w_first_s[(c0 + j) * cin + i], x[i], z);
@@ -246,9 +252,13 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       float y[4] = {0.f, 0.f, 0.f, 0.f};
       // every hidden layer: wait for the layer's accumulator, activate, (re)write the A operand or run the head
       auto layer_prologue = [&](int l) -> const float* {
-        float* sbuf = tail->shift_s[g][l & 1];
-        if (wq < 2) sbuf[col0 + row] = __ldg(sh + (size_t)l * H + col0 + row);
-        ptx::bar_sync(bar_wg, 128);
+        const float* sbuf = sh + (size_t)l * H;
+        if (!pack_rows) {
+          float* stage = tail->shift_s[g][l & 1];
+          if (wq < 2) stage[col0 + row] = __ldg(sh + (size_t)l * H + col0 + row);
+          ptx::bar_sync(bar_wg, 128);
+          sbuf = stage;
+        }
         if (tracer) CNF_TRACE_EVENT(trole, 200 + l);  // start waiting for d_full
         // one warp of the slot polls the mbarrier; the other seven sleep on the hardware barrier (no issue slots)
         if (hf == 0 && wq == 0) ptx::mbar_wait(&tail->d_full[g], d_phase);
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
                                                                       const float* __restrict__ gout,
                                                                       const __half* __restrict__ stash,
                                                                       float* __restrict__ gshift, int64_t T, int64_t P,
-                                                                      int num_stages) {
+                                                                      int num_stages, int pack_rows) {
   constexpr int H = kTc2H;
   constexpr int PREC = CNF_PREC_BF16X3;
   constexpr int kSPL = (H / kSlabK) * 2;
@@ -417,7 +427,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
   const int nl = d.nl, cout = d.cout;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t PB = (P + kTileM - 1) / kTileM;
-  const int64_t tiles = T * PB;
+  const int64_t tiles = tc_num_tiles(T, P, pack_rows);
   const int64_t pairs = (tiles + 1) / 2;
   const int64_t SH = (int64_t)(nl + 1) * H;
 
@@ -457,9 +467,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + g;
       if (tile >= tiles) continue;
-      const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
-      const bool valid = p < P;
-      float* gs = gshift + t * SH;
+      const RowMap rm = tc_row_map(tile, row, T, P, PB, pack_rows);
+      const int64_t t = rm.t, p = rm.p;
+      const bool valid = rm.valid;
       const __half* st_row = stash + (size_t)tile * SH * kTileM + row * 8;  // tile-major stash, see tc_common.cuh
       float gy[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
@@ -481,7 +491,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
           dl[j] = gsum * cs[j];
         }
         tc2_store_a16<PREC>(tmem_a, c0, dl);
-        tc_colsum16_to_global(dl, lane, gs + (size_t)nl * H + c0);
+        tc_colsum16_rows(dl, lane, t, gshift + (size_t)nl * H + c0, SH);
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -510,7 +520,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
 #pragma unroll
           for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
           if (l > 1) tc2_store_a16<PREC>(tmem_a, c0, dl);
-          tc_colsum16_to_global(dl, lane, gs + (size_t)(l - 1) * H + c0);
+          tc_colsum16_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
         }
         ptx::tc_fence_before();
         if (l > 1) {

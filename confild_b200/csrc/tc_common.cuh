@@ -116,6 +116,54 @@ __device__ __forceinline__ void tc_load_cos16(const __half* src, float (&c)[16])
   }
 }
 
+// Which (frame, point) a tile row decodes.  Frame-aligned tiles (default): tile = (frame, 128-point block), rows past P
+// are padding.  Packed tiles (small or ragged P, e.g. the DPS sensor shapes with 10 points per frame): the T*P
+// (frame, point) pairs are numbered consecutively and cut into 128-row tiles, so a tile may span several frames and only
+// the very last tile has padding.  Padding rows are clamped to the last valid pair (safe addresses, results discarded).
+struct RowMap {
+  int64_t t, p;
+  bool valid;
+};
+__device__ __forceinline__ RowMap tc_row_map(int64_t tile, int row, int64_t T, int64_t P, int64_t PB, int packed) {
+  RowMap m;
+  if (packed) {
+    const int64_t R = T * P, q = tile * kTileM + row;
+    m.valid = q < R;
+    const int64_t qq = m.valid ? q : R - 1;
+    m.t = qq / P;
+    m.p = qq - m.t * P;
+  } else {
+    m.t = tile / PB;
+    m.p = (tile - m.t * PB) * kTileM + row;
+    m.valid = m.p < P;
+    if (!m.valid) m.p = P - 1;
+  }
+  return m;
+}
+__host__ __device__ inline int64_t tc_num_tiles(int64_t T, int64_t P, int packed) {
+  return packed ? (T * P + kTileM - 1) / kTileM : T * ((P + kTileM - 1) / kTileM);
+}
+
+// Column sums of a warp's 32 rows when the rows may belong to different frames (packed tiles): `t_lane` is
+// non-decreasing with the lane.  One frame: the plain transpose-reduce; a few frames: one masked reduce per frame;
+// many frames (tiny P): per-row atomics.  `dst0` = gshift + layer/column offset; frame f's row is dst0 + f*SH.
+__device__ __forceinline__ void tc_colsum16_rows(float (&v)[16], int lane, int64_t t_lane, float* dst0, int64_t SH) {
+  const int64_t t_lo = __shfl_sync(0xffffffffu, t_lane, 0), t_hi = __shfl_sync(0xffffffffu, t_lane, 31);
+  if (t_lo == t_hi) {
+    tc_colsum16_to_global(v, lane, dst0 + t_lo * SH);
+  } else if (t_hi - t_lo < 4) {
+    for (int64_t f = t_lo; f <= t_hi; ++f) {
+      float w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = (t_lane == f) ? v[j] : 0.f;
+      tc_colsum16_to_global(w, lane, dst0 + f * SH);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) atomicAdd(dst0 + t_lane * SH + j, v[j]);
+  }
+}
+
 // Raw (still packed) variant for prefetching a whole column range before the accumulator is ready.
 __device__ __forceinline__ void tc_load_cos_chunk(const __half* src, uint4& w) {
   w = __ldg(reinterpret_cast<const uint4*>(src));

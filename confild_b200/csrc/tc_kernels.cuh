@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
                                                                    int64_t coord_frame_stride,
                                                                    const float* __restrict__ shift,
                                                                    OutTargets outs, __half* __restrict__ stash,
-                                                                   int64_t T, int64_t P, int num_stages) {
+                                                                   int64_t T, int64_t P, int num_stages, int pack_rows) {
   using C = TcCfg<H, PREC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
   const int nl = d.nl, cin = d.cin, cout = d.cout;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t PB = (P + kTileM - 1) / kTileM;
-  const int64_t tiles = T * PB;
+  const int64_t tiles = tc_num_tiles(T, P, pack_rows);
   const int64_t SH = (int64_t)(nl + 1) * H;
   const uint32_t tmem_base = tc_setup<H, PREC>(tail, num_stages, warp);
 
@@ -240,8 +240,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
                                                    : reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tail) + 256);
     uint32_t d_phase = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
-      const bool valid = p < P;
+      const RowMap rm = tc_row_map(tile, row, T, P, PB, pack_rows);
+      const int64_t t = rm.t, p = rm.p;
+      const bool valid = rm.valid;
       const float* sh = shift + t * SH;
       float x[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
                                                                     const float* __restrict__ gout,
                                                                     const __half* __restrict__ stash,
                                                                     float* __restrict__ gshift, int64_t T, int64_t P,
-                                                                    int num_stages) {
+                                                                    int num_stages, int pack_rows) {
   constexpr int PREC = CNF_PREC_BF16X3;
   using C = TcCfg<H, PREC>;
   extern __shared__ uint8_t smem_raw[];
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
   const int nl = d.nl, cout = d.cout;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t PB = (P + kTileM - 1) / kTileM;
-  const int64_t tiles = T * PB;
+  const int64_t tiles = tc_num_tiles(T, P, pack_rows);
   const int64_t SH = (int64_t)(nl + 1) * H;
   const uint32_t tmem_base = tc_setup<H, PREC>(tail, num_stages, warp);
 
@@ -416,9 +417,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
     const uint32_t tmem_row = tmem_base + ((uint32_t)(wq * 32) << 16);
     uint32_t d_phase = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int64_t t = tile / PB, p = (tile % PB) * kTileM + row;
-      const bool valid = p < P;
-      float* gs = gshift + t * SH;
+      const RowMap rm = tc_row_map(tile, row, T, P, PB, pack_rows);
+      const int64_t t = rm.t, p = rm.p;
+      const bool valid = rm.valid;
       const __half* st_row = stash + (size_t)tile * SH * kTileM + row * 8;  // tile-major stash, see tc_common.cuh
       float gy[4] = {0.f, 0.f, 0.f, 0.f};
       if (valid) {
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
           dl[j] = g * cs[j];
         }
         tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, dl);
-        tc_colsum16_to_global(dl, lane, gs + (size_t)nl * H + c0);
+        tc_colsum16_rows(dl, lane, t, gshift + (size_t)nl * H + c0, SH);
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
 #pragma unroll
           for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
           if (l > 1) tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, dl);
-          tc_colsum16_to_global(dl, lane, gs + (size_t)(l - 1) * H + c0);
+          tc_colsum16_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
         }
         if (l > 1) {
           ptx::tmem_wait_st();

@@ -191,6 +191,38 @@ def test_gradient_ragged_tiles(case, T, P):
     assert O.rel_l2(g, gwant) <= 1e-2
 
 
+@pytest.mark.parametrize("case,T,P", [("case1", 384, 10), ("case1", 50, 1), ("case1", 7, 300), ("case1", 3, 128),
+                                      ("case4", 40, 10), ("case2", 9, 100), ("case4", 5, 333)])
+@pytest.mark.parametrize("mode", ["auto", "1"])
+def test_packed_tiles_forward_and_gradient(case, T, P, mode, monkeypatch):
+    """f3: DPS sensor shapes (few points per frame).  Packed tiles hold rows of several frames; the forward result and
+    dL/dlatent must equal the oracle's, and (frames being independent) the frame-aligned tiling's."""
+    if mode != "auto":
+        monkeypatch.setenv("CNF_TC_PACKED", mode)
+    dims = O.CASE_SHAPES[case]
+    sd = O.init_params(*dims, seed=0)
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    gout = torch.randn(T, P, dims[2], generator=torch.Generator().manual_seed(7))
+    want = O.forward(sd, coords[None], lat[:, None])
+    gwant = O.grad_latents_from_gout(sd, coords[None], lat[:, None], gout)
+    m = make_model(dims, sd, "bf16x3")
+    l = lat.cuda()[:, None].requires_grad_(True)
+    y = m(coords.cuda()[None], l)
+    (g,) = torch.autograd.grad(y, l, grad_outputs=gout.cuda())
+    torch.cuda.synchronize()
+    assert O.rel_l2(y, want) <= 1e-4
+    assert O.rel_l2(g, gwant) <= 1e-2
+    monkeypatch.setenv("CNF_TC_PACKED", "0")
+    with torch.no_grad():
+        y0 = m(coords.cuda()[None], lat.cuda()[:, None])
+    assert torch.equal(y0, y.detach())  # same arithmetic per row whatever the tiling
+    # per-frame coordinates take the same path
+    monkeypatch.setenv("CNF_TC_PACKED", "1")
+    with torch.no_grad():
+        y1 = m(coords.cuda()[None].expand(T, P, dims[0]).contiguous(), lat.cuda()[:, None])
+    assert torch.equal(y1, y.detach())
+
+
 def test_edge_shapes_and_batch_invariance():
     dims = O.CASE_SHAPES["case1"]
     sd = O.init_params(*dims, seed=0)
