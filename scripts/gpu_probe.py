@@ -114,6 +114,10 @@ if __name__ == "__main__":
         for prec in ("bf16x3", "fp16"):
             timeit("case4", 16, 16384, prec)
         timeit("case1", 16, 16384, "fp32", iters=2)
+    if what == "ragged":
+        for P in (300, 200, 100, 40):
+            timeit("case1", 256, P, "bf16x3")
+        timeit("case4", 64, 300, "bf16x3")
     if what == "case2":
         for prec in ("bf16x3", "fp16"):
             timeit("case2", 32, 16384, prec)
