@@ -163,19 +163,18 @@ int make_tc2_plan(const DeviceInfo& di, int64_t tiles, TcPlan* plan) {
   return CNF_OK;
 }
 
-template <int PREC, bool REDUCE, bool STASH>
+template <int PREC, bool STASH, bool PACKED>
 int launch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs, const float* shift,
                        cnf::OutTargets out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
-  const int pack_rows = use_packed(P);
-  const int64_t tiles = cnf::tc_num_tiles(T, P, pack_rows);
+  const int64_t tiles = cnf::tc_num_tiles(T, P, PACKED ? 1 : 0);
   TcPlan plan;
   if (int rc = make_tc2_plan(di, tiles, &plan)) return rc;
-  auto kern = cnf::tc2_forward_kernel<PREC, REDUCE, STASH>;
+  auto kern = cnf::tc2_forward_kernel<PREC, STASH, PACKED>;
   CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   kern<<<(unsigned)plan.grid, cnf::kTc2Threads, plan.smem, st>>>(d, packed, coords, cfs, shift, out,
-                                                                 reinterpret_cast<__half*>(stash), T, P, plan.stages, pack_rows);
+                                                                 reinterpret_cast<__half*>(stash), T, P, plan.stages);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -183,28 +182,34 @@ int launch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* co
 template <int PREC>
 int dispatch_tc2_forward(const cnf_dims& d, const uint8_t* packed, const float* coords, int64_t cfs,
                          const float* shift, cnf::OutTargets out, void* stash, int64_t T, int64_t P, cudaStream_t st) {
-  const bool reduce = env_int("CNF_TC_REDUCE", 0) != 0;
+  const bool pk = use_packed(P) != 0;
   if (stash)
-    return reduce ? launch_tc2_forward<PREC, true, true>(d, packed, coords, cfs, shift, out, stash, T, P, st)
-                  : launch_tc2_forward<PREC, false, true>(d, packed, coords, cfs, shift, out, stash, T, P, st);
-  return reduce ? launch_tc2_forward<PREC, true, false>(d, packed, coords, cfs, shift, out, stash, T, P, st)
-                : launch_tc2_forward<PREC, false, false>(d, packed, coords, cfs, shift, out, stash, T, P, st);
+    return pk ? launch_tc2_forward<PREC, true, true>(d, packed, coords, cfs, shift, out, stash, T, P, st)
+              : launch_tc2_forward<PREC, true, false>(d, packed, coords, cfs, shift, out, stash, T, P, st);
+  return pk ? launch_tc2_forward<PREC, false, true>(d, packed, coords, cfs, shift, out, stash, T, P, st)
+            : launch_tc2_forward<PREC, false, false>(d, packed, coords, cfs, shift, out, stash, T, P, st);
+}
+
+template <bool PACKED>
+int launch_tc2_backward_t(const cnf_dims& d, const uint8_t* packed, const float* gout, const void* stash, float* gshift,
+                          int64_t T, int64_t P, cudaStream_t st) {
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  const int64_t tiles = cnf::tc_num_tiles(T, P, PACKED ? 1 : 0);
+  TcPlan plan;
+  if (int rc = make_tc2_plan(di, tiles, &plan)) return rc;
+  auto kern = cnf::tc2_backward_kernel<PACKED>;
+  CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  kern<<<(unsigned)plan.grid, cnf::kTc2Threads, plan.smem, st>>>(d, packed, gout, reinterpret_cast<const __half*>(stash),
+                                                                 gshift, T, P, plan.stages);
+  CNF_CUDA(cudaGetLastError());
+  return CNF_OK;
 }
 
 int launch_tc2_backward(const cnf_dims& d, const uint8_t* packed, const float* gout, const void* stash, float* gshift,
                         int64_t T, int64_t P, cudaStream_t st) {
-  DeviceInfo di;
-  if (int rc = device_info(&di)) return rc;
-  const int pack_rows = use_packed(P);
-  const int64_t tiles = cnf::tc_num_tiles(T, P, pack_rows);
-  TcPlan plan;
-  if (int rc = make_tc2_plan(di, tiles, &plan)) return rc;
-  auto kern = cnf::tc2_backward_kernel;
-  CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-  kern<<<(unsigned)plan.grid, cnf::kTc2Threads, plan.smem, st>>>(d, packed, gout, reinterpret_cast<const __half*>(stash),
-                                                                 gshift, T, P, plan.stages, pack_rows);
-  CNF_CUDA(cudaGetLastError());
-  return CNF_OK;
+  return use_packed(P) ? launch_tc2_backward_t<true>(d, packed, gout, stash, gshift, T, P, st)
+                       : launch_tc2_backward_t<false>(d, packed, gout, stash, gshift, T, P, st);
 }
 
 template <int H>

@@ -29,6 +29,7 @@ constexpr int kTc2SlotCols = 256;
 struct Tc2SmemTail {
   float shift_s[2][2][kTc2H];   // [slot][layer parity][column]
   float y_part[2][kTileM][4];   // head partial sums of the upper column half, per slot
+  float y_stage[2][kTileM * 4]; // the tile's decoded values [row][cout], staged for the vectorised store
   float w_first_s[kTc2H * 4];
   float w_out_s[4 * kTc2H];
   uint64_t b_full[kTcMaxStages];
@@ -125,13 +126,15 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
   }
 }
 
-template <int PREC, bool REDUCE, bool STASH>
+template <int PREC, bool STASH, bool PACKED>
 __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
                                                                      const float* __restrict__ coords,
                                                                      int64_t coord_frame_stride,
                                                                      const float* __restrict__ shift,
                                                                      OutTargets outs, __half* __restrict__ stash,
-                                                                     int64_t T, int64_t P, int num_stages, int pack_rows) {
+                                                                     int64_t T, int64_t P, int num_stages) {
+  constexpr bool REDUCE = false;  // hidden-layer arguments stay within ~10 rad: sin.approx is used directly
+  constexpr int pack_rows = PACKED ? 1 : 0;
   constexpr int H = kTc2H;
   constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
   constexpr int kParts = kSplit ? 2 : 1;
@@ -210,12 +213,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       __half* st_row = STASH ? stash + (size_t)tile * SH * kTileM + row * 8 : nullptr;  // see tc_common.cuh
       if (tracer) CNF_TRACE_EVENT(trole, 100);  // tile start
       // FiLM shifts: staged per layer in shared memory (one frame per tile), or read per row from global (packed tiles)
-      const float* s0 = sh;
-      if (!pack_rows) {
+      if (!PACKED) {
         ptx::bar_sync(bar_wg, 128);  // everyone is done with the previous tile's shift buffers
         if (wq < 2) tail->shift_s[g][0][col0 + row] = __ldg(sh + col0 + row);
         ptx::bar_sync(bar_wg, 128);
-        s0 = tail->shift_s[g][0];
       }
 
       // ---- layer 0 on CUDA cores (K = cin), always range-reduced
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         [[maybe_unused]] float cs0[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float z = s0[c0 + j];
+          float z = PACKED ? __ldg(sh + c0 + j) : tail->shift_s[g][0][c0 + j];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (i < cin) z = fmaf(tail->w_first_s[(c0 + j) * cin + i], x[i], z);
@@ -252,8 +253,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       float y[4] = {0.f, 0.f, 0.f, 0.f};
       // every hidden layer: wait for the layer's accumulator, activate, (re)write the A operand or run the head
       auto layer_prologue = [&](int l) -> const float* {
-        const float* sbuf = sh + (size_t)l * H;
-        if (!pack_rows) {
+        const float* sbuf = nullptr;  // packed tiles: the caller reads this row's shifts from global memory
+        if (!PACKED) {
           float* stage = tail->shift_s[g][l & 1];
           if (wq < 2) stage[col0 + row] = __ldg(sh + (size_t)l * H + col0 + row);
           ptx::bar_sync(bar_wg, 128);
@@ -271,8 +272,14 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
 #pragma unroll 1
       for (int l = 1; l < nl; ++l) {
         const float* sbuf = layer_prologue(l);
-        tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, col0, sbuf, tail->w_out_s, cout, y,
-                                                     STASH ? st_row + (size_t)l * H * kTileM : nullptr);
+        // two call sites so that each sees a pointer of known address space (ld.shared vs ld.global, not generic)
+        if (!PACKED)
+          tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, col0, tail->shift_s[g][l & 1], tail->w_out_s,
+                                                       cout, y, STASH ? st_row + (size_t)l * H * kTileM : nullptr);
+        else
+          tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, col0, sh + (size_t)l * H, tail->w_out_s, cout, y,
+                                                       STASH ? st_row + (size_t)l * H * kTileM : nullptr);
+        (void)sbuf;
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tail->a_full[g]);
@@ -280,28 +287,48 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       }
       {
         const float* sbuf = layer_prologue(nl);
-        tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, col0, sbuf, tail->w_out_s, cout, y,
-                                                    STASH ? st_row + (size_t)nl * H * kTileM : nullptr);
+        if (!PACKED)
+          tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, col0, tail->shift_s[g][nl & 1], tail->w_out_s,
+                                                      cout, y, STASH ? st_row + (size_t)nl * H * kTileM : nullptr);
+        else
+          tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, col0, sh + (size_t)nl * H, tail->w_out_s, cout, y,
+                                                      STASH ? st_row + (size_t)nl * H * kTileM : nullptr);
+        (void)sbuf;
         if (tracer) CNF_TRACE_EVENT(trole, 400 + nl);
       }
       // ---- head: combine the two column halves, 12-byte store per point
       ptx::tc_fence_before();
       if (hf == 1) *reinterpret_cast<float4*>(tail->y_part[g][row]) = make_float4(y[0], y[1], y[2], y[3]);
       ptx::bar_sync(bar_slot, 256);
-      if (hf == 0 && valid) {
+      if (hf == 0) {
         const float4 yp = *reinterpret_cast<const float4*>(tail->y_part[g][row]);
         float ys[4] = {y[0] + yp.x, y[1] + yp.y, y[2] + yp.z, y[3] + yp.w};
 #pragma unroll
         for (int o = 0; o < 4; ++o)
           if (o < cout) ys[o] += __ldg(b_out + o);
-        for (int k = 0; k < outs.n; ++k) {  // one target, or every rank's gathered buffer (peer stores over NVLink)
-          float* op = outs.ptr[k] + (t * P + p) * cout;
+        if (outs.n == 1) {  // local target: 4*cout bytes per row straight from registers (L2 merges the sectors)
+          if (valid) {
+            float* op = outs.ptr[0] + (t * P + p) * cout;
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+              if (o < cout) op[o] = ys[o];
+          }
+        } else {
 #pragma unroll
           for (int o = 0; o < 4; ++o)
-            if (o < cout) op[o] = ys[o];
+            if (o < cout) tail->y_stage[g][row * cout + o] = ys[o];
         }
       }
-      __syncwarp();  // rows past P skipped the store: reconverge before the next tile's warp-aligned instructions
+      if (outs.n > 1) {
+        // fused all-gather: peer stores cross NVLink, where partial 32-byte sectors are expensive -- stage the tile and
+        // write its (contiguous) range to every rank's buffer as full 16-byte vectors
+        ptx::bar_sync(bar_slot, 256);
+        int64_t q0;
+        int nvalid;
+        tc_tile_range(tile, T, P, PB, pack_rows, q0, nvalid);
+        tc_store_tile(outs, tail->y_stage[g], q0, nvalid, cout, hf * 128 + row, 256);
+      }
+      __syncwarp();  // the store loops have lane-dependent trip counts: reconverge before warp-aligned instructions
     }
     ptx::tc_fence_before();
   } else if (warp < kMmaWarp + 2) {
@@ -408,11 +435,13 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
 // delta_l (bf16 hi/lo), the accumulator is delta_l * (w0 W_l), and the activation warpgroups multiply by the stashed
 // cos of the layer below, reduce the tile's 128 points per column with a 16-shuffle transpose-reduce per 16 columns
 // and add the column sums into gshift with one red.global per (warp, column).
+template <bool PACKED>
 __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
                                                                       const float* __restrict__ gout,
                                                                       const __half* __restrict__ stash,
                                                                       float* __restrict__ gshift, int64_t T, int64_t P,
-                                                                      int num_stages, int pack_rows) {
+                                                                      int num_stages) {
+  constexpr int pack_rows = PACKED ? 1 : 0;
   constexpr int H = kTc2H;
   constexpr int PREC = CNF_PREC_BF16X3;
   constexpr int kSPL = (H / kSlabK) * 2;
@@ -491,7 +520,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
           dl[j] = gsum * cs[j];
         }
         tc2_store_a16<PREC>(tmem_a, c0, dl);
-        tc_colsum16_rows(dl, lane, t, gshift + (size_t)nl * H + c0, SH);
+        if (PACKED) tc_colsum16_rows(dl, lane, t, gshift + (size_t)nl * H + c0, SH);
+        else tc_colsum16_to_global(dl, lane, gshift + t * SH + (size_t)nl * H + c0);
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -520,7 +550,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
 #pragma unroll
           for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
           if (l > 1) tc2_store_a16<PREC>(tmem_a, c0, dl);
-          tc_colsum16_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
+          if (PACKED) tc_colsum16_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
+          else tc_colsum16_to_global(dl, lane, gshift + t * SH + (size_t)(l - 1) * H + c0);
         }
         ptx::tc_fence_before();
         if (l > 1) {

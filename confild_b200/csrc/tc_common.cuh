@@ -164,6 +164,43 @@ __device__ __forceinline__ void tc_colsum16_rows(float (&v)[16], int lane, int64
   }
 }
 
+// First (frame, point) pair index and number of valid rows of a tile; a tile's valid rows are always a prefix and map
+// to CONSECUTIVE pairs q0, q0+1, ... (frame-aligned tiles stay inside one frame), i.e. to one contiguous range of `out`.
+__device__ __forceinline__ void tc_tile_range(int64_t tile, int64_t T, int64_t P, int64_t PB, int pack_rows, int64_t& q0,
+                                              int& nvalid) {
+  if (pack_rows) {
+    q0 = tile * kTileM;
+    const int64_t left = T * P - q0;
+    nvalid = left < kTileM ? (int)left : kTileM;
+  } else {
+    const int64_t t = tile / PB, p0 = (tile - t * PB) * kTileM;
+    q0 = t * P + p0;
+    const int64_t left = P - p0;
+    nvalid = left < kTileM ? (int)left : kTileM;
+  }
+}
+
+// Cooperative store of a tile's decoded values, staged in shared memory as ys[row*cout + o], to every output target:
+// the range is contiguous, so it goes out as full 16-byte vectors (full 32-byte sectors on the wire -- what matters for
+// the fused all-gather, whose peer stores cross NVLink) with a scalar path for unaligned ranges.
+__device__ __forceinline__ void tc_store_tile(const OutTargets& outs, const float* ys, int64_t q0, int nvalid, int cout,
+                                              int tid, int nthreads) {
+  const int64_t e0 = q0 * cout;
+  const int n = nvalid * cout;
+  if ((e0 & 3) == 0) {
+    const int n4 = n / 4;
+    for (int i = tid; i < n4; i += nthreads) {
+      const float4 v = *reinterpret_cast<const float4*>(ys + 4 * i);
+      for (int k = 0; k < outs.n; ++k) *reinterpret_cast<float4*>(outs.ptr[k] + e0 + 4 * i) = v;
+    }
+    for (int i = 4 * n4 + tid; i < n; i += nthreads)
+      for (int k = 0; k < outs.n; ++k) outs.ptr[k][e0 + i] = ys[i];
+  } else {
+    for (int i = tid; i < n; i += nthreads)
+      for (int k = 0; k < outs.n; ++k) outs.ptr[k][e0 + i] = ys[i];
+  }
+}
+
 // Raw (still packed) variant for prefetching a whole column range before the accumulator is ready.
 __device__ __forceinline__ void tc_load_cos_chunk(const __half* src, uint4& w) {
   w = __ldg(reinterpret_cast<const uint4*>(src));

@@ -59,7 +59,7 @@ struct TcSmemTail {  // lives after the A operand and the weight ring
 template <int H, int PREC>
 __host__ __device__ constexpr size_t tc_smem_bytes(int num_stages) {
   return 1024 /*alignment slack*/ + (size_t)TcCfg<H, PREC>::kABytes + (size_t)num_stages * kStageBytes + 256 +
-         (TcCfg<H, PREC>::kABytes >= 3 * kTileM * 16 ? 0 : 3 * kTileM * 16);
+         (TcCfg<H, PREC>::kABytes >= 4 * kTileM * 16 ? 0 : 4 * kTileM * 16);
 }
 
 // ------------------------------------------------------------------ shared pieces
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     const uint32_t tmem_row = tmem_base + ((uint32_t)(wq * 32) << 16);
     // [3][128] partial head sums: in the A operand's shared memory when there is one (free after the last layer),
     // else (all of A in TMEM) in a dedicated 6 KiB area behind the barriers
-    float4* y_part = C::kABytes >= 3 * kTileM * 16 ? reinterpret_cast<float4*>(a_smem)
+    float4* y_part = C::kABytes >= 4 * kTileM * 16 ? reinterpret_cast<float4*>(a_smem)
                                                    : reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tail) + 256);
     uint32_t d_phase = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
       // ---- head: the four column groups meet in shared memory (the A operand is free until the next tile's layer 0)
       if (cg > 0) y_part[(cg - 1) * kTileM + row] = make_float4(y[0], y[1], y[2], y[3]);
       ptx::bar_sync(1, kTcEpiWarps * 32);
-      if (cg == 0 && valid) {
+      float* y_stage = reinterpret_cast<float*>(y_part + 3 * kTileM);  // [128][cout] right behind the partial sums
+      if (cg == 0) {
         float ys[4] = {y[0], y[1], y[2], y[3]};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -330,12 +331,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
 #pragma unroll
         for (int o = 0; o < 4; ++o)
           if (o < cout) ys[o] += __ldg(b_out + o);
-        for (int k = 0; k < outs.n; ++k) {  // one target, or every rank's gathered buffer (peer stores over NVLink)
-          float* op = outs.ptr[k] + (t * P + p) * cout;
+        if (outs.n == 1) {  // local target: straight from registers
+          if (valid) {
+            float* op = outs.ptr[0] + (t * P + p) * cout;
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+              if (o < cout) op[o] = ys[o];
+          }
+        } else {
 #pragma unroll
           for (int o = 0; o < 4; ++o)
-            if (o < cout) op[o] = ys[o];
+            if (o < cout) y_stage[row * cout + o] = ys[o];
         }
+      }
+      if (outs.n > 1) {  // fused all-gather: contiguous, vectorised stores to every rank's buffer (full sectors on NVLink)
+        ptx::bar_sync(1, kTcEpiWarps * 32);
+        int64_t q0;
+        int nvalid;
+        tc_tile_range(tile, T, P, PB, pack_rows, q0, nvalid);
+        tc_store_tile(outs, y_stage, q0, nvalid, cout, threadIdx.x, kTcEpiWarps * 32);
       }
       __syncwarp();
       ptx::bar_sync(1, kTcEpiWarps * 32);  // partial sums consumed before the next tile's layer 0 overwrites them
