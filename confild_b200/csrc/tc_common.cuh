@@ -187,7 +187,8 @@ __device__ __forceinline__ void tc_store_tile(const OutTargets& outs, const floa
                                               int tid, int nthreads) {
   const int64_t e0 = q0 * cout;
   const int n = nvalid * cout;
-  if ((e0 & 3) == 0) {
+  // every target is the same offset into a (>= 256-byte aligned) buffer, so target 0 decides the alignment
+  if ((reinterpret_cast<uintptr_t>(outs.ptr[0] + e0) & 15) == 0) {
     const int n4 = n / 4;
     for (int i = tid; i < n4; i += nthreads) {
       const float4 v = *reinterpret_cast<const float4*>(ys + 4 * i);
