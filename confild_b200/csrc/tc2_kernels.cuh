@@ -252,13 +252,11 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
 
       float y[4] = {0.f, 0.f, 0.f, 0.f};
       // every hidden layer: wait for the layer's accumulator, activate, (re)write the A operand or run the head
-      auto layer_prologue = [&](int l) -> const float* {
-        const float* sbuf = nullptr;  // packed tiles: the caller reads this row's shifts from global memory
-        if (!PACKED) {
+      auto layer_prologue = [&](int l) {
+        if (!PACKED) {  // stage the layer's FiLM shifts (packed tiles read them per row from global memory instead)
           float* stage = tail->shift_s[g][l & 1];
           if (wq < 2) stage[col0 + row] = __ldg(sh + (size_t)l * H + col0 + row);
           ptx::bar_sync(bar_wg, 128);
-          sbuf = stage;
         }
         if (tracer) CNF_TRACE_EVENT(trole, 200 + l);  // start waiting for d_full
         // one warp of the slot polls the mbarrier; the other seven sleep on the hardware barrier (no issue slots)
@@ -267,11 +265,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         ptx::bar_sync(bar_slot, 256);
         ptx::tc_fence_after();
         if (tracer) CNF_TRACE_EVENT(trole, 300 + l);  // d_full observed
-        return sbuf;
       };
 #pragma unroll 1
       for (int l = 1; l < nl; ++l) {
-        const float* sbuf = layer_prologue(l);
+        layer_prologue(l);
         // two call sites so that each sees a pointer of known address space (ld.shared vs ld.global, not generic)
         if (!PACKED)
           tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, col0, tail->shift_s[g][l & 1], tail->w_out_s,
@@ -279,21 +276,19 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         else
           tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, col0, sh + (size_t)l * H, tail->w_out_s, cout, y,
                                                        STASH ? st_row + (size_t)l * H * kTileM : nullptr);
-        (void)sbuf;
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tail->a_full[g]);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
       }
       {
-        const float* sbuf = layer_prologue(nl);
+        layer_prologue(nl);
         if (!PACKED)
           tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, col0, tail->shift_s[g][nl & 1], tail->w_out_s,
                                                       cout, y, STASH ? st_row + (size_t)nl * H * kTileM : nullptr);
         else
           tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, col0, sh + (size_t)nl * H, tail->w_out_s, cout, y,
                                                       STASH ? st_row + (size_t)nl * H * kTileM : nullptr);
-        (void)sbuf;
         if (tracer) CNF_TRACE_EVENT(trole, 400 + nl);
       }
       // ---- head: combine the two column halves, 12-byte store per point

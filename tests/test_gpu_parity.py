@@ -387,6 +387,44 @@ def test_folded_normalizers_on_gpu():
     assert O.rel_l2(gz, gzc) < 1e-2
 
 
+def test_dps_step_under_cuda_graph():
+    """f3: the per-step CNF work of the DPS loop (forward + stash, sensor loss, backward to the latents) captured once in
+    a CUDA graph and replayed with new latents -- nothing on the path synchronises or allocates outside the graph pool."""
+    dims = O.CASE_SHAPES["case1"]
+    sd = O.init_params(*dims, seed=0)
+    m = make_model(dims, sd, "bf16x3")
+    T, P = 48, 10  # notebook-like: many frames, a handful of sensors
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    c = coords.cuda()[None]
+    y_meas = (torch.randn(T, P, dims[2], generator=torch.Generator().manual_seed(3)) * 0.05).cuda()
+    static_lat = lat.cuda()[:, None].clone().requires_grad_(True)
+
+    def step():
+        y = m(c, static_lat)
+        loss = torch.linalg.norm(y_meas - y)
+        (g,) = torch.autograd.grad(loss, static_lat)
+        return loss.detach(), g
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_g, grad_g = step()
+    for seed in (11, 12):
+        new = torch.randn(T, 1, dims[1], generator=torch.Generator().manual_seed(seed)) * 0.1
+        with torch.no_grad():
+            static_lat.copy_(new.cuda())
+        graph.replay()
+        torch.cuda.synchronize()
+        loss_ref, _, g_ref = O.grad_latents(sd, coords[None], new, lambda y: torch.linalg.norm(y_meas.cpu() - y))
+        assert abs(float(loss_g) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+        assert O.rel_l2(grad_g, g_ref) <= 1e-2
+
+
 def test_training_mode_with_grad_raises():
     m = cb.SIRENAutodecoder_film(2, 128, 3, 10, 128).cuda()  # training mode, params require grad
     with pytest.raises(NotImplementedError):
