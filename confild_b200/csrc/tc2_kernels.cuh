@@ -34,6 +34,7 @@ struct Tc2SmemTail {
   float w_out_s[4 * kTc2H];
   uint64_t b_full[kTcMaxStages];
   uint64_t b_empty[kTcMaxStages];
+  uint64_t a_half[2];  // K slab 0 of the slot's A operand written and its accumulator drained (forward kernel)
   uint64_t a_full[2];
   uint64_t d_full[2];
   uint64_t turn[2];  // issue token passed between the two MMA issuer warps
@@ -81,32 +82,51 @@ __device__ __forceinline__ void tc2_store_a16(uint32_t tmem_a, int c0, const flo
   if (kSplit) ptx::tmem_st_32x32b_x8(tmem_a + 64 + c0 / 2, lo);
 }
 
+// Columns of a warpgroup (column half hf), in the order it produces them: groups 0,1 lie in K slab 0 of the next
+// layer's A operand (columns 0-63), groups 2,3 in K slab 1, so the first half of the next layer's MMAs can start
+// when every warp is half-way through its epilogue.
+__device__ __forceinline__ constexpr int tc2_group_col(int hf, int c) { return 32 * hf + 16 * (c & 1) + 64 * (c >> 1); }
+
 // One hidden layer for this thread's row and its warpgroup's 64 columns.
 // Software pipeline over four 16-column groups: the TMEM load of group c+2 and the sines (MUFU) of group c+1 are issued
 // before the bf16 split / pack (ALU) of group c, so the XU and ALU pipes overlap inside the warp.
+// Unless LAST, arrives on `a_half` once the whole accumulator row is in registers and K slab 0 of the A operand is
+// written (the issuer may then overwrite D with the first 12 MMAs of the next layer), and on `a_full` at the end.
 template <int PREC, bool REDUCE, bool LAST, bool STASH>
-__device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tmem_a, int col0,
+__device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tmem_a, int hf,
                                                  const float* __restrict__ sbuf, const float* __restrict__ w_out_s,
-                                                 int cout, float (&y)[4], __half* stash_l) {
+                                                 int cout, float (&y)[4], __half* stash_l, uint64_t* a_half,
+                                                 uint64_t* a_full) {
   uint32_t v[2][16];
   float hcur[16], hnext[16];
-  ptx::tmem_ld_32x32b_x16(lane_base + col0, v[0]);
+  ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, 0), v[0]);
   ptx::tmem_wait_ld();
-  ptx::tmem_ld_32x32b_x16(lane_base + col0 + 16, v[1]);
-  tc_sines16<REDUCE, STASH>(v[0], sbuf + col0, hnext, STASH ? stash_l + (size_t)col0 * kTileM : nullptr);
+  ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, 1), v[1]);
+  tc_sines16<REDUCE, STASH>(v[0], sbuf + tc2_group_col(hf, 0), hnext,
+                             STASH ? stash_l + (size_t)tc2_group_col(hf, 0) * kTileM : nullptr);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const int c0 = col0 + c * 16;
+    const int c0 = tc2_group_col(hf, c);
 #pragma unroll
     for (int j = 0; j < 16; ++j) hcur[j] = hnext[j];
     if (c + 1 < 4) {
+      const int c1 = tc2_group_col(hf, c + 1);
       ptx::tmem_wait_ld();
-      tc_sines16<REDUCE, STASH>(v[(c + 1) & 1], sbuf + c0 + 16, hnext,
-                                 STASH ? stash_l + (size_t)(c0 + 16) * kTileM : nullptr);
-      if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(lane_base + c0 + 32, v[c & 1]);
+      tc_sines16<REDUCE, STASH>(v[(c + 1) & 1], sbuf + c1, hnext, STASH ? stash_l + (size_t)c1 * kTileM : nullptr);
+      if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, c + 2), v[c & 1]);
     }
     if (!LAST) {
       tc2_store_a16<PREC>(tmem_a, c0, hcur);
+      if (c == 1) {
+        ptx::tmem_wait_ld();  // group 3 (the last of D) is in registers
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(a_half);
+      } else if (c == 3) {
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(a_full);
+      }
     } else {
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
@@ -160,8 +180,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       ptx::mbar_init(&tail->b_empty[s], 2);  // released by the commits of both slots' issuers
     }
     for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(&tail->a_half[g], 256);
       ptx::mbar_init(&tail->a_full[g], 256);
-      ptx::mbar_init(&tail->d_full[g], 1);
+      ptx::mbar_init(&tail->d_full[g], 2);  // one commit per issuer warp (K slab 0, K slab 1)
       ptx::mbar_init(&tail->turn[g], 1);
     }
     ptx::fence_mbar_init();
@@ -183,10 +204,11 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
 
   if (warp < kTc2EpiWarps) {
     // ===================== activation warpgroups =====================
-    // warpgroup (g, hf): tile slot g, columns [64*hf, 64*hf + 64); thread = TMEM lane / query point `row`.
+    // warpgroup (g, hf): tile slot g, columns [32*hf, +32) of K slab 0 and [64 + 32*hf, +32) of K slab 1 (see
+    // tc2_group_col); thread = TMEM lane / query point `row`.
     const int g = warp / 8, hf = (warp / 4) & 1, wq = warp % 4;
     const int row = wq * 32 + lane;
-    const int col0 = 64 * hf;
+    const int stage_col = 32 * hf + (row & 31) + 64 * ((row >> 5) & 1);  // column whose shift this thread stages (wq < 2)
     const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + g * kTc2SlotCols;
     const uint32_t tmem_a = lane_base + 128;
     const float* b_out = reinterpret_cast<const float*>(packed + lay.b_out);
@@ -215,13 +237,14 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       // FiLM shifts: staged per layer in shared memory (one frame per tile), or read per row from global (packed tiles)
       if (!PACKED) {
         ptx::bar_sync(bar_wg, 128);  // everyone is done with the previous tile's shift buffers
-        if (wq < 2) tail->shift_s[g][0][col0 + row] = __ldg(sh + col0 + row);
+        if (wq < 2) tail->shift_s[g][0][stage_col] = __ldg(sh + stage_col);
         ptx::bar_sync(bar_wg, 128);
       }
 
       // ---- layer 0 on CUDA cores (K = cin), always range-reduced
 #pragma unroll 1
-      for (int c0 = col0; c0 < col0 + 64; c0 += 32) {
+      for (int half = 0; half < 2; ++half) {
+        const int c0 = 32 * hf + 64 * half;
         float h[32];
         [[maybe_unused]] float cs0[32];
 #pragma unroll
@@ -244,10 +267,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
             tc_stash16(st_row + (size_t)(c0 + q * 16) * kTileM, c16);
           }
         }
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(half == 0 ? &tail->a_half[g] : &tail->a_full[g]);  // K slab `half` of the A operand is in TMEM
       }
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tail->a_full[g]);
       if (tracer) CNF_TRACE_EVENT(trole, 101);  // layer 0 done, a_full arrived
 
       float y[4] = {0.f, 0.f, 0.f, 0.f};
@@ -255,7 +278,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       auto layer_prologue = [&](int l) {
         if (!PACKED) {  // stage the layer's FiLM shifts (packed tiles read them per row from global memory instead)
           float* stage = tail->shift_s[g][l & 1];
-          if (wq < 2) stage[col0 + row] = __ldg(sh + (size_t)l * H + col0 + row);
+          if (wq < 2) stage[stage_col] = __ldg(sh + (size_t)l * H + stage_col);
           ptx::bar_sync(bar_wg, 128);
         }
         if (tracer) CNF_TRACE_EVENT(trole, 200 + l);  // start waiting for d_full
@@ -271,24 +294,24 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         layer_prologue(l);
         // two call sites so that each sees a pointer of known address space (ld.shared vs ld.global, not generic)
         if (!PACKED)
-          tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, col0, tail->shift_s[g][l & 1], tail->w_out_s,
-                                                       cout, y, STASH ? st_row + (size_t)l * H * kTileM : nullptr);
+          tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][l & 1], tail->w_out_s, cout,
+                                                       y, STASH ? st_row + (size_t)l * H * kTileM : nullptr,
+                                                       &tail->a_half[g], &tail->a_full[g]);
         else
-          tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, col0, sh + (size_t)l * H, tail->w_out_s, cout, y,
-                                                       STASH ? st_row + (size_t)l * H * kTileM : nullptr);
-        ptx::tmem_wait_st();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&tail->a_full[g]);
+          tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, hf, sh + (size_t)l * H, tail->w_out_s, cout, y,
+                                                       STASH ? st_row + (size_t)l * H * kTileM : nullptr,
+                                                       &tail->a_half[g], &tail->a_full[g]);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
       }
       {
         layer_prologue(nl);
         if (!PACKED)
-          tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, col0, tail->shift_s[g][nl & 1], tail->w_out_s,
-                                                      cout, y, STASH ? st_row + (size_t)nl * H * kTileM : nullptr);
+          tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][nl & 1], tail->w_out_s, cout,
+                                                      y, STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr,
+                                                      nullptr);
         else
-          tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, col0, sh + (size_t)nl * H, tail->w_out_s, cout, y,
-                                                      STASH ? st_row + (size_t)nl * H * kTileM : nullptr);
+          tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, hf, sh + (size_t)nl * H, tail->w_out_s, cout, y,
+                                                      STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr, nullptr);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + nl);
       }
       // ---- head: combine the two column halves, 12-byte store per point
@@ -327,71 +350,82 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
     }
     ptx::tc_fence_before();
   } else if (warp < kMmaWarp + 2) {
-    // ===================== MMA issuers (one warp per tile slot) =====================
-    // Each warp walks the (uniform) schedule of its slot and polls the barriers; one elected lane issues.  Keeping
-    // the control flow converged keeps every tcgen05 operand in uniform registers: a divergent single-lane loop
-    // (R2UR moves + a waterfall loop per MMA) cannot sustain one UTCHMMA per ~85 clk.  Two issuers keep the tensor
-    // pipe's queue fed back to back: while one waits for its slot's A operand the other is issuing.
-    const int g = warp - kMmaWarp;
+    // ===================== MMA issuers (one warp per K slab) =====================
+    // A layer of a slot is issued as two halves, one per K slab of the A operand: half 0 as soon as the slot's
+    // activation warps have drained the accumulator and written slab 0 (a_half), half 1 when they are done (a_full),
+    // so half of the layer's MMAs overlap the slot's own epilogue.  The halves go out in the fixed order
+    //   (slot 0, half 0) (slot 0, half 1) (slot 1, half 0) (slot 1, half 1) (slot 0, half 0 of the next layer) ...
+    // which keeps the two slots half a period apart: one slot's epilogue runs under the other slot's MMAs.
+    // Warp `half` issues every half-`half`, and an issue token (turn[]) ping-pongs between the two warps.  A warp that
+    // has issued MMAs is held back until the tensor pipe has taken them (their descriptors live in its uniform
+    // registers), so consecutive halves must come from DIFFERENT warps: the next warp has already waited for its
+    // operands and only needs the token.  Each warp polls with all lanes (converged control flow keeps the tcgen05
+    // operands in uniform registers; a divergent single-lane loop cannot sustain the issue rate); one elected lane
+    // issues.  The tensor pipe executes in issue order; d_full[g] counts one commit per warp, so it completes only
+    // when both halves of the layer have finished.
+    const int half = warp - kMmaWarp;
+    constexpr int kSPH = kSPL / 2;  // stages per half: hi, lo of one K slab (one stage for fp16)
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t ring_addr = ptx::smem_u32(ring);
-    const uint32_t tmem_d = tmem_u + g * kTc2SlotCols;
-    const uint32_t tmem_a = tmem_d + 128;
-    uint32_t a_phase = 0u;
-    uint32_t turn_phase = g == 0 ? 1u : 0u;  // slot 0 issues first (a fresh barrier passes a parity-1 wait)
-    int slot0 = 0;       // ring slot of stage 0 of the current layer
-    uint32_t ph0 = 0;    // its mbarrier parity
+    uint32_t a_phase[2] = {0u, 0u};
+    uint32_t turn_phase = half == 0 ? 1u : 0u;  // half 0 issues first (a fresh barrier passes a parity-1 wait)
+    int slot0 = half * kSPH;  // ring slot of this warp's first stage of the current layer
+    uint32_t ph0 = 0;         // its mbarrier parity
     CNF_TRACE_DECL;
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-      const bool mine = (2 * pair + g < tiles);  // an odd tile count leaves slot 1 idle in the last pair
       for (int l = 1; l <= nl; ++l) {
-        // 1. everything this layer needs, waited for BEFORE taking the issue token
-        if (mine) {
+        {  // this K slab's weights (shared by both slots): they landed long ago, the ring is three layers deep
           int slot = slot0;
           uint32_t ph = ph0;
 #pragma unroll
-          for (int s = 0; s < kSPL; ++s) {  // weights first: they landed long ago (the ring is three layers deep)
+          for (int s = 0; s < kSPH; ++s) {
             ptx::mbar_wait(&tail->b_full[slot], ph);
-            if (++slot == num_stages) { slot = 0; ph ^= 1u; }
+            if (++slot >= num_stages) { slot = 0; ph ^= 1u; }
           }
-          if (lane == 0) CNF_TRACE_EVENT(2 + g, 1000 + l);  // start waiting a_full[g]
-          ptx::mbar_wait(&tail->a_full[g], a_phase);
-          a_phase ^= 1u;
-          if (lane == 0) CNF_TRACE_EVENT(2 + g, 2000 + l);  // operands ready
         }
-        // 2. strict alternation slot 0, slot 1, slot 0, ... : the epilogue of one slot overlaps the MMAs of the other
-        ptx::mbar_wait(&tail->turn[g], turn_phase);
-        turn_phase ^= 1u;
-        ptx::tc_fence_after();
-        // 3. the layer's MMAs back to back (24 for the bf16 split, 8 for fp16), then hand the token over
-        if (ptx::elect_one()) {
-          int slot = slot0;
 #pragma unroll
-          for (int s = 0; s < kSPL; ++s) {
-            if (mine) {
-              const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
-              const int ks = s / kParts, part = s % kParts;
+        for (int g = 0; g < 2; ++g) {
+          const bool mine = (2 * pair + g < tiles);  // an odd tile count leaves slot 1 idle in the last pair
+          const uint32_t tmem_d = tmem_u + g * kTc2SlotCols;
+          const uint32_t tmem_a = tmem_d + 128;
+          if (mine) {
+            if (lane == 0) CNF_TRACE_EVENT(2 + half, 1000 + 500 * g + l);  // start waiting for the A operand
+            ptx::mbar_wait(half == 0 ? &tail->a_half[g] : &tail->a_full[g], a_phase[g]);
+            a_phase[g] ^= 1u;
+            if (lane == 0) CNF_TRACE_EVENT(2 + half, 2000 + 500 * g + l);  // operands ready
+          }
+          ptx::mbar_wait(&tail->turn[half], turn_phase);
+          turn_phase ^= 1u;
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            int slot = slot0;
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint32_t a_hi = tmem_a + (ks * 4 + kk) * 8;  // 16 K elements = 8 packed columns
-                if (part == 0) {
-                  ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (ks | kk) != 0);
-                  if (kSplit) ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
-                } else {
-                  ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
+            for (int s = 0; s < kSPH; ++s) {
+              if (mine) {
+                const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+                const int part = s % kParts;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint32_t a_hi = tmem_a + (half * 4 + kk) * 8;  // 16 K elements = 8 packed columns
+                  if (part == 0) {
+                    ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (uint32_t)((half | kk) != 0));
+                    if (kSplit) ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
+                  } else {
+                    ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
+                  }
                 }
+                ptx::umma_commit(&tail->b_empty[slot]);
+              } else {
+                ptx::mbar_arrive(&tail->b_empty[slot]);  // idle slot: still release its share of the stage
               }
-              ptx::umma_commit(&tail->b_empty[slot]);
-            } else {
-              ptx::mbar_arrive(&tail->b_empty[slot]);  // idle slot: still release its share of the stage
+              if (++slot >= num_stages) slot = 0;
             }
-            if (++slot == num_stages) slot = 0;
+            if (mine) ptx::umma_commit(&tail->d_full[g]);
+            ptx::mbar_arrive(&tail->turn[half ^ 1]);
           }
-          if (mine) ptx::umma_commit(&tail->d_full[g]);
-          ptx::mbar_arrive(&tail->turn[g ^ 1]);
+          __syncwarp();
+          if (mine && lane == 0) CNF_TRACE_EVENT(2 + half, 3000 + 500 * g + l);  // this half issued + committed
         }
-        __syncwarp();
-        if (mine && lane == 0) CNF_TRACE_EVENT(2 + g, 3000 + l);  // all MMAs of (g,l) issued + committed
         slot0 += kSPL;
         if (slot0 >= num_stages) { slot0 -= num_stages; ph0 ^= 1u; }
       }

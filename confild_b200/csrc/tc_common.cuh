@@ -22,15 +22,17 @@ struct OutTargets {
 #ifdef CNF_TRACE
 // Debug build only: per-role event trace of CTA 0 (role r writes (code, clock64) pairs at trace[r*8192 + 2*n]).
 __device__ unsigned long long* g_trace = nullptr;
-__device__ __forceinline__ void trace_event(int role, int& n, unsigned long long code) {
-  if (g_trace != nullptr && blockIdx.x == 0 && n < 4000) {
-    g_trace[role * 8192 + 2 * n] = code;
-    g_trace[role * 8192 + 2 * n + 1] = clock64();
+__device__ __forceinline__ void trace_event(unsigned long long* buf, int role, int& n, unsigned long long code) {
+  if (buf != nullptr && n < 4000) {  // two fire-and-forget stores: the pointer was fetched once, at kernel start
+    buf[role * 8192 + 2 * n] = code;
+    buf[role * 8192 + 2 * n + 1] = clock64();
     ++n;
   }
 }
-#define CNF_TRACE_DECL int trace_n = 0
-#define CNF_TRACE_EVENT(role, code) trace_event(role, trace_n, code)
+#define CNF_TRACE_DECL \
+  int trace_n = 0;     \
+  unsigned long long* trace_p = (blockIdx.x == 0) ? g_trace : nullptr
+#define CNF_TRACE_EVENT(role, code) trace_event(trace_p, role, trace_n, code)
 #else
 #define CNF_TRACE_DECL
 #define CNF_TRACE_EVENT(role, code)

@@ -24,8 +24,7 @@ import collections
 ev = {}
 for role in range(20):
     ev[role] = [(int(c), int(t) - t0) for c, t in b[role] if t > 0]
-# MMA thread = role 2; epilogue warps = role 4 + warp
-mma0, mma1 = ev[2], ev[3]
+# issuer warp of K slab h = role 2 + h (events 1000/2000/3000 + 500*slot + layer); epilogue warps = role 4 + warp
 def nth(evs, code, n):
     k = 0
     for c, t in evs:
@@ -37,10 +36,13 @@ TILE = 3
 for l in (3, 4, 5):
     print(f"--- tile-pair #{TILE}, layer {l}")
     for g in (0, 1):
-        mma = mma0 if g == 0 else mma1
-        a_obs = nth(mma, 2000 + l, TILE); issued = nth(mma, 3000 + l, TILE)
-        a_obs_next = nth(mma, 2000 + l + 1, TILE)
-        print(f"  MMA slot {g}: a_full seen {a_obs}, issued+committed {issued} (+{issued - a_obs}); next a_full seen {a_obs_next}")
-        for w in range(8 * g, 8 * g + 8):
+        row = []
+        for h in (0, 1):
+            w = nth(ev[2 + h], 1000 + 500 * g + l, TILE); r = nth(ev[2 + h], 2000 + 500 * g + l, TILE)
+            i = nth(ev[2 + h], 3000 + 500 * g + l, TILE)
+            row.append(f"half{h} wait {w} ready {r} issued {i}")
+            last = i
+        print(f"  slot {g}: " + " | ".join(row))
+        for w in range(8 * g, 8 * g + 8, 4):
             d = nth(ev[4 + w], 300 + l, TILE); e = nth(ev[4 + w], 400 + l, TILE)
-            print(f"    warp {w:2d} (hf={(w // 4) % 2} wq={w % 4}): d_full seen {d} (+{d - issued}), epilogue done {e} (E={e - d})")
+            print(f"    warp {w:2d} (hf={(w // 4) % 2} wq={w % 4}): d_full seen {d} (+{d - last}), epilogue done {e} (E={e - d})")
