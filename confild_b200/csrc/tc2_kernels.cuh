@@ -92,11 +92,14 @@ __device__ __forceinline__ constexpr int tc2_group_col(int hf, int c) { return 3
 // before the bf16 split / pack (ALU) of group c, so the XU and ALU pipes overlap inside the warp.
 // Unless LAST, arrives on `a_half` once the whole accumulator row is in registers and K slab 0 of the A operand is
 // written (the issuer may then overwrite D with the first 12 MMAs of the next layer), and on `a_full` at the end.
-template <int PREC, bool REDUCE, bool LAST, bool STASH>
+struct Tc2NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+template <int PREC, bool REDUCE, bool LAST, bool STASH, typename HalfHook = Tc2NoHook>
 __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tmem_a, int hf,
                                                  const float* __restrict__ sbuf, const float* __restrict__ w_out_s,
                                                  int cout, float (&y)[4], __half* stash_l, uint64_t* a_half,
-                                                 uint64_t* a_full) {
+                                                 uint64_t* a_full, HalfHook on_half = HalfHook()) {
   uint32_t v[2][16];
   float hcur[16], hnext[16];
   ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, 0), v[0]);
@@ -122,6 +125,7 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(a_half);
+        on_half();  // debug trace hook (empty in product builds)
       } else if (c == 3) {
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
@@ -289,18 +293,23 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         ptx::tc_fence_after();
         if (tracer) CNF_TRACE_EVENT(trole, 300 + l);  // d_full observed
       };
+      [[maybe_unused]] int cur_layer = 0;
+      auto half_hook = [&]() {
+        if (tracer) CNF_TRACE_EVENT(trole, 350 + cur_layer);  // a_half arrived
+      };
 #pragma unroll 1
       for (int l = 1; l < nl; ++l) {
         layer_prologue(l);
+        cur_layer = l;
         // two call sites so that each sees a pointer of known address space (ld.shared vs ld.global, not generic)
         if (!PACKED)
           tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][l & 1], tail->w_out_s, cout,
                                                        y, STASH ? st_row + (size_t)l * H * kTileM : nullptr,
-                                                       &tail->a_half[g], &tail->a_full[g]);
+                                                       &tail->a_half[g], &tail->a_full[g], half_hook);
         else
           tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, hf, sh + (size_t)l * H, tail->w_out_s, cout, y,
                                                        STASH ? st_row + (size_t)l * H * kTileM : nullptr,
-                                                       &tail->a_half[g], &tail->a_full[g]);
+                                                       &tail->a_half[g], &tail->a_full[g], half_hook);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
       }
       {

@@ -239,6 +239,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     float4* y_part = C::kABytes >= 4 * kTileM * 16 ? reinterpret_cast<float4*>(a_smem)
                                                    : reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tail) + 256);
     uint32_t d_phase = 0;
+    CNF_TRACE_DECL;
+    const bool tracer = (lane == 0);
+    [[maybe_unused]] const int trole = 4 + warp;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const RowMap rm = tc_row_map(tile, row, T, P, PB, pack_rows);
       const int64_t t = rm.t, p = rm.p;
@@ -281,6 +284,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
       for (int l = 1; l <= nl; ++l) {
         const float* shl = sh + (size_t)l * H;
         tc_wait_d_full(tail, warp, d_phase);
+        if (tracer) CNF_TRACE_EVENT(trole, 300 + l);  // d_full observed
         const bool last = (l == nl);
 #pragma unroll 1
         for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         } else {
           ptx::tc_fence_before();
         }
+        if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
       }
       // ---- head: the four column groups meet in shared memory (the A operand is free until the next tile's layer 0)
       if (cg > 0) y_part[(cg - 1) * kTileM + row] = make_float4(y[0], y[1], y[2], y[3]);
@@ -361,12 +366,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int slot = 0;
     uint32_t b_phase = 0, a_phase = 0;
+    CNF_TRACE_DECL;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       for (int l = 1; l <= nl; ++l) {
         ptx::mbar_wait(&tail->a_full, a_phase);
         a_phase ^= 1u;
+        if (lane == 0) CNF_TRACE_EVENT(2, 2000 + l);  // A operand ready
         ptx::tc_fence_after();
         tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
+        if (lane == 0) CNF_TRACE_EVENT(2, 3000 + l);  // the layer's MMAs issued and committed
       }
     }
     __syncwarp();

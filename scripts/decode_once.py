@@ -20,6 +20,8 @@ with torch.no_grad():
     for _ in range(5):
         y = m(c, l)
     e1.record()
+    y_ref = y.clone()
+    same = all(torch.equal(m(c, l), y_ref) for _ in range(6))
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 msg = f"{case} T={T} P={P} {prec}: {ms:.3f} ms -> {T * P / ms / 1e6:.4f} G pf/s"
@@ -27,4 +29,4 @@ if len(sys.argv) > 5 and sys.argv[5] == "check":
     n = min(P, 4096)
     want = O.forward(sd, coords[None, :n], lat[:2, None])
     msg += f"  rel_l2 vs oracle {O.rel_l2(y[:2, :n].cpu(), want):.3e}"
-print(msg, flush=True)
+print(msg + f"  bitwise reproducible over 6 reruns: {same}", flush=True)

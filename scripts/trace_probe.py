@@ -44,5 +44,5 @@ for l in (3, 4, 5):
             last = i
         print(f"  slot {g}: " + " | ".join(row))
         for w in range(8 * g, 8 * g + 8, 4):
-            d = nth(ev[4 + w], 300 + l, TILE); e = nth(ev[4 + w], 400 + l, TILE)
-            print(f"    warp {w:2d} (hf={(w // 4) % 2} wq={w % 4}): d_full seen {d} (+{d - last}), epilogue done {e} (E={e - d})")
+            d = nth(ev[4 + w], 300 + l, TILE); e = nth(ev[4 + w], 400 + l, TILE); hh = nth(ev[4 + w], 350 + l, TILE)
+            print(f"    warp {w:2d} (hf={(w // 4) % 2} wq={w % 4}): d_full seen {d} (+{d - last}), a_half arrived {hh} (+{hh - d}), epilogue done {e} (E={e - d})")
