@@ -8,9 +8,10 @@
 //               tcgen05.ld of the fp32 accumulator 16 columns at a time, + FiLM shift, MUFU sin, split into bf16 hi/lo
 //               (or fp16), 16-byte conflict-free st.shared into the next layer's A operand; last layer: partial dot
 //               with the output head, the four column groups meet in shared memory.
-//   warp 16     MMA issuer: the whole warp walks the schedule, one elected lane issues tcgen05.mma (M=128, N=128, K=16,
-//               both operands from shared memory) for every (row block, K slab, hi/lo pass); accumulators in TMEM.
-//   warp 17     one lane streams the pre-swizzled 16 KiB weight stages from L2 with 1-D bulk TMA copies.
+//   warp 16     MMA issuer: the whole warp walks the schedule, one elected lane issues tcgen05.mma (M=128, N=256/128,
+//               K=16) for every (K slab, hi/lo pass, row-block set); accumulators in TMEM.
+//   warp 17     second MMA issuer of the H=256 forward kernel (see kHalfOverlap); idle otherwise.
+//   warp 18     one lane streams the pre-swizzled 16 KiB weight stages from L2 with 1-D bulk TMA copies.
 // Hand-shakes: b_full/b_empty per ring slot, a_full (A operand written, 512 arrivals), d_full (layer's MMAs done).
 // Sixteen activation warps (four per SM sub-partition) bring the epilogue to the MUFU bound; MMA and epilogue of a tile
 // do not overlap here (a second 128 x H operand does not fit: 2 x 192 KB at H = 384).
@@ -25,7 +26,7 @@
 namespace cnf {
 
 constexpr int kTcEpiWarps = 16;
-constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
+constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;
 
 template <int H, int PREC>
 struct TcCfg {
@@ -43,6 +44,10 @@ struct TcCfg {
   static constexpr int kABytes = kParts * kAPartBytes;
   static constexpr int kStagesPerLayer = kNBlocks * kSlabs * kParts;
   static constexpr int kColsPerGroup = H / 4;  // columns per activation column group
+  // H=256 forward: all of A is TMEM-resident and a thread owns four 16-column groups, so (as in the H=128 kernel) the
+  // epilogue can drain its accumulator row into registers half-way and let the first K half of the next layer's MMAs
+  // run under its second half.  Column group cg then owns [32cg, 32cg+32) of K half 0 and [128+32cg, +32) of K half 1.
+  static constexpr bool kHalfOverlap = (H == 256);
   static constexpr uint32_t kTmemCols = (H + kATmemCols) <= 256 ? 256u : 512u;
   static constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, kStageRows);
   static_assert(kColsPerGroup % 16 == 0, "column groups are processed 16 columns at a time");
@@ -53,6 +58,8 @@ struct TcSmemTail {  // lives after the A operand and the weight ring
   uint64_t b_empty[kTcMaxStages];
   uint64_t a_full;
   uint64_t d_full;
+  uint64_t a_half;   // kHalfOverlap: accumulator drained and K half 0 of the A operand written
+  uint64_t turn[2];  // kHalfOverlap: issue token passed between the two MMA issuer warps
   uint32_t tmem_base;
 };
 
@@ -173,7 +180,7 @@ __device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, uint32_t tmem_row,
 
 // Common prologue: barriers, TMEM allocation.  Returns the TMEM base.
 template <int H, int PREC>
-__device__ __forceinline__ uint32_t tc_setup(TcSmemTail* tail, int num_stages, int warp) {
+__device__ __forceinline__ uint32_t tc_setup(TcSmemTail* tail, int num_stages, int warp, uint32_t d_full_count = 1) {
   using C = TcCfg<H, PREC>;
   if (threadIdx.x == 0) {
     for (int s = 0; s < num_stages; ++s) {
@@ -181,7 +188,10 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmemTail* tail, int num_stages, i
       ptx::mbar_init(&tail->b_empty[s], 1);
     }
     ptx::mbar_init(&tail->a_full, kTcEpiWarps * 32);
-    ptx::mbar_init(&tail->d_full, 1);
+    ptx::mbar_init(&tail->d_full, d_full_count);
+    ptx::mbar_init(&tail->a_half, kTcEpiWarps * 32);
+    ptx::mbar_init(&tail->turn[0], 1);
+    ptx::mbar_init(&tail->turn[1], 1);
     ptx::fence_mbar_init();
   }
   if (warp == kTcEpiWarps) {
@@ -200,6 +210,117 @@ __device__ __forceinline__ void tc_wait_d_full(TcSmemTail* tail, int warp, uint3
   d_phase ^= 1u;
   ptx::bar_sync(1, kTcEpiWarps * 32);
   ptx::tc_fence_after();
+}
+
+// ------------------------------------------------------------------ H = 256 forward: half-layer overlap
+__device__ __forceinline__ constexpr int tc_half_col(int cg, int c) { return 32 * cg + 16 * (c & 1) + 128 * (c >> 1); }
+
+// One hidden layer for this thread's row and its column group's 64 columns (kHalfOverlap).  Software pipeline over four
+// 16-column groups (TMEM load of group c+2 and sines of group c+1 before the split / pack of group c); after group 1
+// the accumulator row is in registers and K half 0 of the next A operand is written: arrive on a_half, so the issuer may
+// overwrite D with the first half of the next layer's MMAs while groups 2,3 are finished; a_full at the end.
+template <int H, int PREC, bool REDUCE, bool LAST, bool STASH>
+__device__ __forceinline__ void tc_hidden_layer_half(uint8_t* a_smem, uint32_t tmem_row, int row, int cg,
+                                                     const float* __restrict__ shl, const float* __restrict__ w_out,
+                                                     int cout, float (&y)[4], __half* stash_l, TcSmemTail* tail) {
+  uint32_t v[2][16];
+  float hcur[16], hnext[16];
+  ptx::tmem_ld_32x32b_x16(tmem_row + tc_half_col(cg, 0), v[0]);
+  ptx::tmem_wait_ld();
+  ptx::tmem_ld_32x32b_x16(tmem_row + tc_half_col(cg, 1), v[1]);
+  tc_sines16<REDUCE, STASH>(v[0], shl + tc_half_col(cg, 0), hnext,
+                             STASH ? stash_l + (size_t)tc_half_col(cg, 0) * kTileM : nullptr);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int c0 = tc_half_col(cg, c);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) hcur[j] = hnext[j];
+    if (c + 1 < 4) {
+      const int c1 = tc_half_col(cg, c + 1);
+      ptx::tmem_wait_ld();
+      tc_sines16<REDUCE, STASH>(v[(c + 1) & 1], shl + c1, hnext, STASH ? stash_l + (size_t)c1 * kTileM : nullptr);
+      if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(tmem_row + tc_half_col(cg, c + 2), v[c & 1]);
+    }
+    if (!LAST) {
+      tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, hcur);
+      if (c == 1) {
+        ptx::tmem_wait_ld();  // group 3 (the last of D) is in registers
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tail->a_half);
+      } else if (c == 3) {
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tail->a_full);
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        if (o >= cout) continue;
+        float acc = y[o];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_out + (size_t)o * H + c0) + q);
+          acc = fmaf(w4.x, hcur[q * 4 + 0], acc);
+          acc = fmaf(w4.y, hcur[q * 4 + 1], acc);
+          acc = fmaf(w4.z, hcur[q * 4 + 2], acc);
+          acc = fmaf(w4.w, hcur[q * 4 + 3], acc);
+        }
+        y[o] = acc;
+      }
+    }
+  }
+}
+
+// Issue K half `half` (K slabs [2*half, 2*half+2), all of A in TMEM) of one hidden layer; called by issuer warp `half`
+// as a whole converged warp.  `slot`/`phase` point at this half's first weight group in the ring and are advanced past
+// the whole layer.  Order of halves: (layer l, half 0) (l, half 1) (l+1, half 0) ... under the ping-pong token.
+template <int H, int PREC>
+__device__ __forceinline__ void tc_issue_half(int half, uint32_t ring_addr, uint32_t tmem_d, TcSmemTail* tail,
+                                              int num_stages, int& slot, uint32_t& phase, uint32_t& a_phase,
+                                              uint32_t& turn_phase) {
+  using C = TcCfg<H, PREC>;
+  constexpr int NB = C::kNBlocks;  // 2
+  constexpr uint32_t kIdescWide = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kTileM, 256);
+  constexpr int kGroupsPerHalf = (C::kSlabs / 2) * C::kParts;
+  auto advance = [&](int groups) {
+    slot += groups * NB;
+    if (slot >= num_stages) { slot -= num_stages; phase ^= 1u; }
+  };
+  if (half == 1) advance(kGroupsPerHalf);  // skip the other warp's groups
+  ptx::mbar_wait(half == 0 ? &tail->a_half : &tail->a_full, a_phase);
+  a_phase ^= 1u;
+  ptx::mbar_wait(&tail->turn[half], turn_phase);
+  turn_phase ^= 1u;
+#pragma unroll
+  for (int k2 = 0; k2 < C::kSlabs / 2; ++k2) {
+    const int ks = half * (C::kSlabs / 2) + k2;
+    const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
+#pragma unroll
+    for (int part = 0; part < C::kParts; ++part) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) ptx::mbar_wait(&tail->b_full[slot + j], phase);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t first = (part == 0) ? (uint32_t)((ks | kk) != 0) : 1u;
+          ptx::umma_f16_ts(tmem_d, at_hi + kk * 8, b + 2 * kk, kIdescWide, first);
+          if (C::kSplit && part == 0) ptx::umma_f16_ts(tmem_d, at_hi + 64 + kk * 8, b + 2 * kk, kIdescWide, 1u);
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) ptx::umma_commit(&tail->b_empty[slot + j]);
+        if (k2 == C::kSlabs / 2 - 1 && part == C::kParts - 1) {
+          ptx::umma_commit(&tail->d_full);  // d_full counts one commit per issuer warp
+          ptx::mbar_arrive(&tail->turn[half ^ 1]);
+        }
+      }
+      __syncwarp();
+      advance(1);
+    }
+  }
+  if (half == 0) advance(kGroupsPerHalf);
 }
 
 // ------------------------------------------------------------------ forward
@@ -223,7 +344,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
   const int64_t PB = (P + kTileM - 1) / kTileM;
   const int64_t tiles = tc_num_tiles(T, P, pack_rows);
   const int64_t SH = (int64_t)(nl + 1) * H;
-  const uint32_t tmem_base = tc_setup<H, PREC>(tail, num_stages, warp);
+  const uint32_t tmem_base = tc_setup<H, PREC>(tail, num_stages, warp, C::kHalfOverlap ? 2u : 1u);
 
   if (warp < kTcEpiWarps) {
     // ===================== activation warps =====================
@@ -258,7 +379,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
 
       // ---- layer 0: K = cin on CUDA cores, always range-reduced (|arg| reaches tens of radians)
 #pragma unroll 1
-      for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
+      for (int c = 0; c < C::kColsPerGroup / 16; ++c) {
+        const int c0 = C::kHalfOverlap ? tc_half_col(cg, c) : col_lo + c * 16;
         float h[16];
         [[maybe_unused]] float cs[16];
 #pragma unroll
@@ -273,6 +395,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         }
         tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
         if (STASH) tc_stash16(st_row + (size_t)c0 * kTileM, cs);
+        if (C::kHalfOverlap && c == 1) {  // K half 0 of the A operand is written (D of the previous tile is long drained)
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tail->a_half);
+        }
       }
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
@@ -286,39 +413,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         tc_wait_d_full(tail, warp, d_phase);
         if (tracer) CNF_TRACE_EVENT(trole, 300 + l);  // d_full observed
         const bool last = (l == nl);
-#pragma unroll 1
-        for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
-          uint32_t v[16];
-          ptx::tmem_ld_32x32b_x16(tmem_row + c0, v);
-          ptx::tmem_wait_ld();
-          float h[16];
-          tc_sines16<REDUCE, STASH>(v, shl + c0, h, STASH ? st_row + ((size_t)l * H + c0) * kTileM : nullptr);
+        if constexpr (C::kHalfOverlap) {
+          __half* stl = STASH ? st_row + (size_t)l * H * kTileM : nullptr;
           if (!last) {
-            tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
+            tc_hidden_layer_half<H, PREC, REDUCE, false, STASH>(a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
           } else {
+            tc_hidden_layer_half<H, PREC, REDUCE, true, STASH>(a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+            ptx::tc_fence_before();
+          }
+        } else {
+#pragma unroll 1
+          for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld_32x32b_x16(tmem_row + c0, v);
+            ptx::tmem_wait_ld();
+            float h[16];
+            tc_sines16<REDUCE, STASH>(v, shl + c0, h, STASH ? st_row + ((size_t)l * H + c0) * kTileM : nullptr);
+            if (!last) {
+              tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
+            } else {
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              if (o >= cout) continue;
-              float acc = y[o];
+              for (int o = 0; o < 4; ++o) {
+                if (o >= cout) continue;
+                float acc = y[o];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_out + (size_t)o * H + c0) + q);
-                acc = fmaf(w4.x, h[q * 4 + 0], acc);
-                acc = fmaf(w4.y, h[q * 4 + 1], acc);
-                acc = fmaf(w4.z, h[q * 4 + 2], acc);
-                acc = fmaf(w4.w, h[q * 4 + 3], acc);
+                for (int q = 0; q < 4; ++q) {
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_out + (size_t)o * H + c0) + q);
+                  acc = fmaf(w4.x, h[q * 4 + 0], acc);
+                  acc = fmaf(w4.y, h[q * 4 + 1], acc);
+                  acc = fmaf(w4.z, h[q * 4 + 2], acc);
+                  acc = fmaf(w4.w, h[q * 4 + 3], acc);
+                }
+                y[o] = acc;
               }
-              y[o] = acc;
             }
           }
-        }
-        if (!last) {
-          ptx::tmem_wait_st();
-          ptx::tc_fence_before();
-          ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&tail->a_full);
-        } else {
-          ptx::tc_fence_before();
+          if (!last) {
+            ptx::tmem_wait_st();
+            ptx::tc_fence_before();
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(&tail->a_full);
+          } else {
+            ptx::tc_fence_before();
+          }
         }
         if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
       }
@@ -360,21 +497,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
       ptx::bar_sync(1, kTcEpiWarps * 32);  // partial sums consumed before the next tile's layer 0 overwrites them
     }
     ptx::tc_fence_before();
-  } else if (warp == kTcEpiWarps) {
-    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+  } else if (warp < kTcEpiWarps + 2) {
+    // ===================== MMA issuers (whole warps, one elected lane issues) =====================
+    const int which = warp - kTcEpiWarps;
     const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int slot = 0;
     uint32_t b_phase = 0, a_phase = 0;
     CNF_TRACE_DECL;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      for (int l = 1; l <= nl; ++l) {
-        ptx::mbar_wait(&tail->a_full, a_phase);
-        a_phase ^= 1u;
-        if (lane == 0) CNF_TRACE_EVENT(2, 2000 + l);  // A operand ready
-        ptx::tc_fence_after();
-        tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
-        if (lane == 0) CNF_TRACE_EVENT(2, 3000 + l);  // the layer's MMAs issued and committed
+    if constexpr (C::kHalfOverlap) {
+      // warp `which` issues K half `which` of every layer; consecutive halves come from different warps (a warp that
+      // has issued MMAs is held until the tensor pipe has taken them), ordered by a ping-pong token
+      uint32_t turn_phase = which == 0 ? 1u : 0u;  // half 0 first (a fresh barrier passes a parity-1 wait)
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int l = 1; l <= nl; ++l) {
+          tc_issue_half<H, PREC>(which, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase, turn_phase);
+          if (lane == 0) CNF_TRACE_EVENT(2 + which, 3000 + l);  // this warp's half of the layer issued and committed
+        }
+      }
+    } else if (which == 0) {
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int l = 1; l <= nl; ++l) {
+          ptx::mbar_wait(&tail->a_full, a_phase);
+          a_phase ^= 1u;
+          if (lane == 0) CNF_TRACE_EVENT(2, 2000 + l);  // A operand ready
+          ptx::tc_fence_after();
+          tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
+          if (lane == 0) CNF_TRACE_EVENT(2, 3000 + l);  // the layer's MMAs issued and committed
+        }
       }
     }
     __syncwarp();
@@ -502,6 +652,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
         }
       }
     }
+  } else if (warp == kTcEpiWarps + 1) {
+    // second issuer warp: unused by the backward kernel
   } else if (warp == kTcEpiWarps) {
     const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
