@@ -10,7 +10,7 @@
 //               with the output head, the four column groups meet in shared memory.
 //   warp 16     MMA issuer: the whole warp walks the schedule, one elected lane issues tcgen05.mma (M=128, N=256/128,
 //               K=16) for every (K slab, hi/lo pass, row-block set); accumulators in TMEM.
-//   warp 17     second MMA issuer of the H=256 forward kernel (see kHalfOverlap); idle otherwise.
+//   warp 17     second MMA issuer of the H=256/384 forward kernels (see kHalfOverlap); idle otherwise.
 //   warp 18     one lane streams the pre-swizzled 16 KiB weight stages from L2 with 1-D bulk TMA copies.
 // Hand-shakes: b_full/b_empty per ring slot, a_full (A operand written, 512 arrivals), d_full (layer's MMAs done).
 // Sixteen activation warps (four per SM sub-partition) bring the epilogue to the MUFU bound; MMA and epilogue of a tile
@@ -44,10 +44,13 @@ struct TcCfg {
   static constexpr int kABytes = kParts * kAPartBytes;
   static constexpr int kStagesPerLayer = kNBlocks * kSlabs * kParts;
   static constexpr int kColsPerGroup = H / 4;  // columns per activation column group
-  // H=256 forward: all of A is TMEM-resident and a thread owns four 16-column groups, so (as in the H=128 kernel) the
-  // epilogue can drain its accumulator row into registers half-way and let the first K half of the next layer's MMAs
-  // run under its second half.  Column group cg then owns [32cg, 32cg+32) of K half 0 and [128+32cg, +32) of K half 1.
-  static constexpr bool kHalfOverlap = (H == 256);
+  // Forward overlap (H = 256, 384): column group cg owns columns [64c + 16cg, +16) of every K slab c, i.e. its c-th
+  // 16-column group belongs to K slab c of the next layer's A operand.  After kEarlyGroups groups a thread holds the rest
+  // of its accumulator row in registers (two groups, software pipeline) and arrives on a_half: the first kEarlyGroups K
+  // slabs of the next layer's MMAs then run under the rest of the epilogue (half of it at H=256, a third at H=384).
+  static constexpr bool kHalfOverlap = (H == 256 || H == 384);
+  static constexpr int kGroups = kColsPerGroup / 16;                 // 16-column groups per thread = K slabs
+  static constexpr int kEarlyGroups = kGroups >= 4 ? kGroups - 2 : kGroups;
   static constexpr uint32_t kTmemCols = (H + kATmemCols) <= 256 ? 256u : 512u;
   static constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, kStageRows);
   static_assert(kColsPerGroup % 16 == 0, "column groups are processed 16 columns at a time");
@@ -58,7 +61,7 @@ struct TcSmemTail {  // lives after the A operand and the weight ring
   uint64_t b_empty[kTcMaxStages];
   uint64_t a_full;
   uint64_t d_full;
-  uint64_t a_half;   // kHalfOverlap: accumulator drained and K half 0 of the A operand written
+  uint64_t a_half;   // kHalfOverlap: accumulator drained and the first K slabs of the A operand written
   uint64_t turn[2];  // kHalfOverlap: issue token passed between the two MMA issuer warps
   uint32_t tmem_base;
 };
@@ -74,17 +77,18 @@ __host__ __device__ constexpr size_t tc_smem_bytes(int num_stages) {
 // elected lane issues, which keeps the tcgen05 operands in uniform registers (a divergent single-lane loop pays R2UR
 // moves and a waterfall loop per MMA and cannot keep the tensor pipe fed).  `slot`/`phase` walk the weight ring.
 template <int H, int PREC>
-__device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_addr, uint32_t tmem_d, TcSmemTail* tail,
-                                               int num_stages, int& slot, uint32_t& phase) {
+__device__ __forceinline__ void tc_issue_slabs(int ks_begin, int ks_end, uint32_t a_addr, uint32_t ring_addr,
+                                               uint32_t tmem_d, TcSmemTail* tail, int num_stages, int& slot,
+                                               uint32_t& phase) {
   using C = TcCfg<H, PREC>;
   constexpr int NB = C::kNBlocks;
   // One weight "group" = the NB adjacent ring slots holding all 128-row blocks of one (K slab, hi/lo part).  Row blocks
-  // 0 and 1 are contiguous in shared memory, so they feed ONE N=256 MMA (145/175 clk instead of 2 x 85/116); a third
-  // block (H=384) gets an N=128 MMA into the next accumulator columns, which also interleaves independent accumulators.
+  // 0 and 1 are contiguous in shared memory, so they feed ONE N=256 MMA (128 clk instead of 2 x 66-72); a third block
+  // (H=384) gets an N=128 MMA into the next accumulator columns, which also interleaves independent accumulators.
   constexpr uint32_t kIdescWide = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kTileM, NB >= 2 ? 256 : 128);
   constexpr uint32_t kIdescTail = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kTileM, 128);
 #pragma unroll 1
-  for (int ks = 0; ks < C::kSlabs; ++ks) {
+  for (int ks = ks_begin; ks < ks_end; ++ks) {
     const bool a_in_tmem = ks < 2 * C::kATmemBlocks;
     // A from TMEM: K slab ks = columns [64*ks, 64*ks+64) of block ks/2 -> 8 packed columns per K=16 step
     const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
@@ -128,6 +132,12 @@ __device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_ad
       if (slot >= num_stages) { slot = 0; phase ^= 1u; }
     }
   }
+}
+
+template <int H, int PREC>
+__device__ __forceinline__ void tc_issue_layer(uint32_t a_addr, uint32_t ring_addr, uint32_t tmem_d, TcSmemTail* tail,
+                                               int num_stages, int& slot, uint32_t& phase) {
+  tc_issue_slabs<H, PREC>(0, TcCfg<H, PREC>::kSlabs, a_addr, ring_addr, tmem_d, tail, num_stages, slot, phase);
   if (ptx::elect_one()) ptx::umma_commit(&tail->d_full);
   __syncwarp();
 }
@@ -212,45 +222,51 @@ __device__ __forceinline__ void tc_wait_d_full(TcSmemTail* tail, int warp, uint3
   ptx::tc_fence_after();
 }
 
-// ------------------------------------------------------------------ H = 256 forward: half-layer overlap
-__device__ __forceinline__ constexpr int tc_half_col(int cg, int c) { return 32 * cg + 16 * (c & 1) + 128 * (c >> 1); }
+// ------------------------------------------------------------------ forward overlap (H = 256, 384)
+template <int H>
+__device__ __forceinline__ constexpr int tc_slab_col(int cg, int c) { return 64 * c + 16 * cg; }
 
-// One hidden layer for this thread's row and its column group's 64 columns (kHalfOverlap).  Software pipeline over four
-// 16-column groups (TMEM load of group c+2 and sines of group c+1 before the split / pack of group c); after group 1
-// the accumulator row is in registers and K half 0 of the next A operand is written: arrive on a_half, so the issuer may
-// overwrite D with the first half of the next layer's MMAs while groups 2,3 are finished; a_full at the end.
+// One hidden layer for this thread's row and its column group's 16-column groups (kHalfOverlap), one group per K slab.
+// Software pipeline (TMEM load of group c+2 and sines of group c+1 before the split / pack / store of group c); after
+// group kEarlyGroups-1 the rest of the accumulator row is in registers and the first kEarlyGroups K slabs of the next
+// A operand are written: arrive on a_half, so the issuer may overwrite D with that part of the next layer's MMAs while
+// the last two groups are finished; a_full at the end.
 template <int H, int PREC, bool REDUCE, bool LAST, bool STASH>
-__device__ __forceinline__ void tc_hidden_layer_half(uint8_t* a_smem, uint32_t tmem_row, int row, int cg,
-                                                     const float* __restrict__ shl, const float* __restrict__ w_out,
-                                                     int cout, float (&y)[4], __half* stash_l, TcSmemTail* tail) {
+__device__ __forceinline__ void tc_hidden_layer_overlap(uint8_t* a_smem, uint32_t tmem_row, int row, int cg,
+                                                        const float* __restrict__ shl, const float* __restrict__ w_out,
+                                                        int cout, float (&y)[4], __half* stash_l, TcSmemTail* tail) {
+  using C = TcCfg<H, PREC>;
+  constexpr int NG = C::kGroups;
   uint32_t v[2][16];
   float hcur[16], hnext[16];
-  ptx::tmem_ld_32x32b_x16(tmem_row + tc_half_col(cg, 0), v[0]);
+  ptx::tmem_ld_32x32b_x16(tmem_row + tc_slab_col<H>(cg, 0), v[0]);
   ptx::tmem_wait_ld();
-  ptx::tmem_ld_32x32b_x16(tmem_row + tc_half_col(cg, 1), v[1]);
-  tc_sines16<REDUCE, STASH>(v[0], shl + tc_half_col(cg, 0), hnext,
-                             STASH ? stash_l + (size_t)tc_half_col(cg, 0) * kTileM : nullptr);
+  ptx::tmem_ld_32x32b_x16(tmem_row + tc_slab_col<H>(cg, 1), v[1]);
+  tc_sines16<REDUCE, STASH>(v[0], shl + tc_slab_col<H>(cg, 0), hnext,
+                             STASH ? stash_l + (size_t)tc_slab_col<H>(cg, 0) * kTileM : nullptr);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int c0 = tc_half_col(cg, c);
+  for (int c = 0; c < NG; ++c) {
+    const int c0 = tc_slab_col<H>(cg, c);
 #pragma unroll
     for (int j = 0; j < 16; ++j) hcur[j] = hnext[j];
-    if (c + 1 < 4) {
-      const int c1 = tc_half_col(cg, c + 1);
+    if (c + 1 < NG) {
+      const int c1 = tc_slab_col<H>(cg, c + 1);
       ptx::tmem_wait_ld();
       tc_sines16<REDUCE, STASH>(v[(c + 1) & 1], shl + c1, hnext, STASH ? stash_l + (size_t)c1 * kTileM : nullptr);
-      if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(tmem_row + tc_half_col(cg, c + 2), v[c & 1]);
+      if (c + 2 < NG) ptx::tmem_ld_32x32b_x16(tmem_row + tc_slab_col<H>(cg, c + 2), v[c & 1]);
     }
     if (!LAST) {
       tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, hcur);
-      if (c == 1) {
-        ptx::tmem_wait_ld();  // group 3 (the last of D) is in registers
+      if (c == C::kEarlyGroups - 1) {
+        ptx::tmem_wait_ld();  // the last group of D is in registers
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
+        if (C::kABytes > 0) ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&tail->a_half);
-      } else if (c == 3) {
+      } else if (c == NG - 1) {
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
+        if (C::kABytes > 0) ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&tail->a_full);
       }
     } else {
@@ -272,55 +288,35 @@ __device__ __forceinline__ void tc_hidden_layer_half(uint8_t* a_smem, uint32_t t
   }
 }
 
-// Issue K half `half` (K slabs [2*half, 2*half+2), all of A in TMEM) of one hidden layer; called by issuer warp `half`
-// as a whole converged warp.  `slot`/`phase` point at this half's first weight group in the ring and are advanced past
-// the whole layer.  Order of halves: (layer l, half 0) (l, half 1) (l+1, half 0) ... under the ping-pong token.
+// Issue one part of a hidden layer: issuer warp 0 the first kEarlyGroups K slabs (after a_half), issuer warp 1 the rest
+// (after a_full); each called as a whole converged warp.  `slot`/`phase` point at the layer's first weight group and are
+// advanced past the whole layer.  Order: (layer l, part 0) (l, part 1) (l+1, part 0) ... under the ping-pong token:
+// consecutive parts come from different warps because a warp that has issued MMAs is held until the tensor pipe has
+// taken them.  d_full counts one commit per issuer warp.
 template <int H, int PREC>
-__device__ __forceinline__ void tc_issue_half(int half, uint32_t ring_addr, uint32_t tmem_d, TcSmemTail* tail,
-                                              int num_stages, int& slot, uint32_t& phase, uint32_t& a_phase,
-                                              uint32_t& turn_phase) {
+__device__ __forceinline__ void tc_issue_part(int which, uint32_t a_addr, uint32_t ring_addr, uint32_t tmem_d,
+                                              TcSmemTail* tail, int num_stages, int& slot, uint32_t& phase,
+                                              uint32_t& a_phase, uint32_t& turn_phase) {
   using C = TcCfg<H, PREC>;
-  constexpr int NB = C::kNBlocks;  // 2
-  constexpr uint32_t kIdescWide = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kTileM, 256);
-  constexpr int kGroupsPerHalf = (C::kSlabs / 2) * C::kParts;
-  auto advance = [&](int groups) {
-    slot += groups * NB;
-    if (slot >= num_stages) { slot -= num_stages; phase ^= 1u; }
+  constexpr int kEarly = C::kEarlyGroups;  // K slabs of part 0
+  auto skip = [&](int slabs) {
+    slot += slabs * C::kParts * C::kNBlocks;
+    while (slot >= num_stages) { slot -= num_stages; phase ^= 1u; }
   };
-  if (half == 1) advance(kGroupsPerHalf);  // skip the other warp's groups
-  ptx::mbar_wait(half == 0 ? &tail->a_half : &tail->a_full, a_phase);
+  if (which == 1) skip(kEarly);
+  ptx::mbar_wait(which == 0 ? &tail->a_half : &tail->a_full, a_phase);
   a_phase ^= 1u;
-  ptx::mbar_wait(&tail->turn[half], turn_phase);
+  ptx::mbar_wait(&tail->turn[which], turn_phase);
   turn_phase ^= 1u;
-#pragma unroll
-  for (int k2 = 0; k2 < C::kSlabs / 2; ++k2) {
-    const int ks = half * (C::kSlabs / 2) + k2;
-    const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
-#pragma unroll
-    for (int part = 0; part < C::kParts; ++part) {
-#pragma unroll
-      for (int j = 0; j < NB; ++j) ptx::mbar_wait(&tail->b_full[slot + j], phase);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint32_t first = (part == 0) ? (uint32_t)((ks | kk) != 0) : 1u;
-          ptx::umma_f16_ts(tmem_d, at_hi + kk * 8, b + 2 * kk, kIdescWide, first);
-          if (C::kSplit && part == 0) ptx::umma_f16_ts(tmem_d, at_hi + 64 + kk * 8, b + 2 * kk, kIdescWide, 1u);
-        }
-#pragma unroll
-        for (int j = 0; j < NB; ++j) ptx::umma_commit(&tail->b_empty[slot + j]);
-        if (k2 == C::kSlabs / 2 - 1 && part == C::kParts - 1) {
-          ptx::umma_commit(&tail->d_full);  // d_full counts one commit per issuer warp
-          ptx::mbar_arrive(&tail->turn[half ^ 1]);
-        }
-      }
-      __syncwarp();
-      advance(1);
-    }
+  ptx::tc_fence_after();
+  tc_issue_slabs<H, PREC>(which == 0 ? 0 : kEarly, which == 0 ? kEarly : C::kSlabs, a_addr, ring_addr, tmem_d, tail,
+                          num_stages, slot, phase);
+  if (ptx::elect_one()) {
+    ptx::umma_commit(&tail->d_full);
+    ptx::mbar_arrive(&tail->turn[which ^ 1]);
   }
-  if (half == 0) advance(kGroupsPerHalf);
+  __syncwarp();
+  if (which == 0) skip(C::kSlabs - kEarly);
 }
 
 // ------------------------------------------------------------------ forward
@@ -380,7 +376,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
       // ---- layer 0: K = cin on CUDA cores, always range-reduced (|arg| reaches tens of radians)
 #pragma unroll 1
       for (int c = 0; c < C::kColsPerGroup / 16; ++c) {
-        const int c0 = C::kHalfOverlap ? tc_half_col(cg, c) : col_lo + c * 16;
+        const int c0 = C::kHalfOverlap ? tc_slab_col<H>(cg, c) : col_lo + c * 16;
         float h[16];
         [[maybe_unused]] float cs[16];
 #pragma unroll
@@ -395,9 +391,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         }
         tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
         if (STASH) tc_stash16(st_row + (size_t)c0 * kTileM, cs);
-        if (C::kHalfOverlap && c == 1) {  // K half 0 of the A operand is written (D of the previous tile is long drained)
+        if (C::kHalfOverlap && c == C::kEarlyGroups - 1) {  // the first K slabs of the A operand are written
           ptx::tmem_wait_st();
           ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(&tail->a_half);
         }
       }
@@ -416,9 +413,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         if constexpr (C::kHalfOverlap) {
           __half* stl = STASH ? st_row + (size_t)l * H * kTileM : nullptr;
           if (!last) {
-            tc_hidden_layer_half<H, PREC, REDUCE, false, STASH>(a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+            tc_hidden_layer_overlap<H, PREC, REDUCE, false, STASH>(a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
           } else {
-            tc_hidden_layer_half<H, PREC, REDUCE, true, STASH>(a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+            tc_hidden_layer_overlap<H, PREC, REDUCE, true, STASH>(a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
             ptx::tc_fence_before();
           }
         } else {
@@ -506,12 +503,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     uint32_t b_phase = 0, a_phase = 0;
     CNF_TRACE_DECL;
     if constexpr (C::kHalfOverlap) {
-      // warp `which` issues K half `which` of every layer; consecutive halves come from different warps (a warp that
-      // has issued MMAs is held until the tensor pipe has taken them), ordered by a ping-pong token
+      // warp `which` issues part `which` of every layer (see tc_issue_part), ordered by a ping-pong token
       uint32_t turn_phase = which == 0 ? 1u : 0u;  // half 0 first (a fresh barrier passes a parity-1 wait)
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         for (int l = 1; l <= nl; ++l) {
-          tc_issue_half<H, PREC>(which, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase, turn_phase);
+          tc_issue_part<H, PREC>(which, a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase, turn_phase);
           if (lane == 0) CNF_TRACE_EVENT(2 + which, 3000 + l);  // this warp's half of the layer issued and committed
         }
       }
