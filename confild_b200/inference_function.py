@@ -24,6 +24,29 @@ def _frames_per_chunk(t_size: int, m_size: int, cout: int, batch_size: int) -> i
     return max(int(batch_size), min(t_size, CHUNK_OUTPUT_BYTES // per_frame), 1)
 
 
+#: decoded tiles (128 points) that fill the GPU for a couple of waves: the smallest chunk the tail of a decode tapers to
+_MIN_CHUNK_TILES = 1024
+
+
+def _chunk_plan(t_size: int, m_size: int, cout: int, batch_size: int) -> list:
+    """Frames per launch for ``decoder``: full chunks, then a geometric taper (/3 per chunk) down to a GPU-filling minimum.
+
+    The device->host copy of chunk i runs under the decode of chunk i+1; per output byte the copy is ~3x faster than the
+    decode, so a chunk a third the size of its predecessor still hides the predecessor's copy, and only the copy of the
+    last (smallest) chunk is exposed at the end instead of a full 128 MiB one.
+    """
+    step = _frames_per_chunk(t_size, m_size, cout, batch_size)
+    tiles_per_frame = max(1, (m_size + 127) // 128)
+    n = max(1, -(-_MIN_CHUNK_TILES // tiles_per_frame))
+    rev, rem = [], int(t_size)
+    while rem > 0:
+        take = min(n, rem, step)
+        rev.append(take)
+        rem -= take
+        n = min(step, n * 3)
+    return rev[::-1]
+
+
 def _out_features(model) -> int:
     return int(model.net1[-1].weight.shape[0])
 
@@ -56,7 +79,7 @@ def decoder(coords, latents, model, x_normalizer, y_normalizer, batch_size, devi
     m_size, coords_size = coords.shape
     cout = _out_features(model)
     dev = torch.device(device)
-    step = _frames_per_chunk(t_size, m_size, cout, batch_size)
+    step = _frames_per_chunk(t_size, m_size, cout, batch_size)  # CPU tensors only (the module then raises)
     if out is None:
         out = torch.empty((t_size, m_size, cout), dtype=torch.float32, pin_memory=(dev.type == "cuda"))
     with torch.no_grad():
@@ -69,17 +92,22 @@ def decoder(coords, latents, model, x_normalizer, y_normalizer, batch_size, devi
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         pending = []
-        for sid in range(0, t_size, step):
-            lat = latents[sid:sid + step].reshape(-1, 1, latent_size).to(dev)
+        sid = 0
+        # one upload of all latents (T*L*4 bytes, tiny next to the field): a per-chunk synchronous copy would make the
+        # host wait for the previous chunk's kernel before it can enqueue the next one
+        lat_dev = latents.reshape(-1, 1, latent_size).to(dev, non_blocking=True)
+        for n in _chunk_plan(t_size, m_size, cout, batch_size):
+            lat = lat_dev[sid:sid + n]
             chunk = y_normalizer.denormalize(model(coords_n, lat))
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done)
-                out[sid:sid + chunk.shape[0]].copy_(chunk, non_blocking=True)
+                out[sid:sid + n].copy_(chunk, non_blocking=True)
                 chunk.record_stream(copy_stream)
             pending.append(chunk)
             if len(pending) > 2:  # bound the number of in-flight device chunks
                 pending.pop(0)
+            sid += n
         copy_stream.synchronize()
     return out

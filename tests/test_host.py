@@ -156,3 +156,16 @@ def test_fold_normalizers_matches_explicit_affines(xm, ym):
     got = O.forward(folded.state_dict(), coords, lat)
     assert torch.allclose(got, want, rtol=1e-10, atol=1e-10)
     assert not torch.equal(folded.net1[0].weight, m.net1[0].weight) or xm == "none"
+
+
+@pytest.mark.parametrize("T,P,cout,bs", [(1024, 65536, 3, 16), (7, 300, 3, 16), (1, 1, 2, 1), (3, 65536, 4, 1),
+                                         (2000, 1000, 3, 64), (16, 16384, 3, 4), (513, 10, 3, 256)])
+def test_decoder_chunk_plan_covers_all_frames_and_tapers(T, P, cout, bs):
+    from confild_b200.inference_function import _chunk_plan, _frames_per_chunk
+    plan = _chunk_plan(T, P, cout, bs)
+    step = _frames_per_chunk(T, P, cout, bs)
+    assert sum(plan) == T and all(0 < n <= step for n in plan)
+    # after the first (remainder) chunk sizes never grow, and the tail shrinks by at most 3x per chunk, so every
+    # device->host copy hides under the next chunk's decode
+    for a, b in zip(plan[1:], plan[2:]):
+        assert b <= a and 3 * b >= a
