@@ -222,6 +222,12 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
 
+// Residuals x - bf16(x) of the two values packed in `hi` (cvt.rn.bf16x2: x0 in the low half), packed as bf16x2.
+// One fma.f32x2 for both columns (exact: x - h = fma(h, -1, x)) instead of two scalar subtractions.
+__device__ __forceinline__ float2 bf16x2_residual(uint32_t hi, float x0, float x1) {
+  return __ffma2_rn(make_float2(bf16lo_to_f32(hi), bf16hi_to_f32(hi)), make_float2(-1.f, -1.f), make_float2(x0, x1));
+}
+
 // "Pinned" variants: volatile asm keeps the program order of MUFU and pack instructions relative to each other, so a
 // software-pipelined epilogue (sines of group j+1 issued before the packs of group j) survives the scheduler.
 __device__ __forceinline__ float sin_approx_pinned(float x) {

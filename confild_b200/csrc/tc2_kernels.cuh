@@ -54,7 +54,8 @@ __device__ __forceinline__ void tc2_store_a(uint32_t tmem_a, int c0, const float
     const float x0 = h[2 * e], x1 = h[2 * e + 1];
     if (kSplit) {
       hi[e] = ptx::pack_bf16x2(x0, x1);
-      lo[e] = ptx::pack_bf16x2(x0 - ptx::bf16lo_to_f32(hi[e]), x1 - ptx::bf16hi_to_f32(hi[e]));
+      const float2 r = ptx::bf16x2_residual(hi[e], x0, x1);
+        lo[e] = ptx::pack_bf16x2(r.x, r.y);
     } else {
       hi[e] = ptx::pack_f16x2(x0, x1);
     }
@@ -73,7 +74,9 @@ __device__ __forceinline__ void tc2_store_a16(uint32_t tmem_a, int c0, const flo
     const float x0 = h[2 * e], x1 = h[2 * e + 1];
     if (kSplit) {
       hi[e] = ptx::pack_bf16x2_pinned(x0, x1);
-      lo[e] = ptx::pack_bf16x2_pinned(x0 - ptx::bf16lo_to_f32(hi[e]), x1 - ptx::bf16hi_to_f32(hi[e]));
+      // residual x - bf16(x) of both columns in one fma.f32x2 (exact: x - h = fma(h, -1, x))
+      const float2 r = ptx::bf16x2_residual(hi[e], x0, x1);
+      lo[e] = ptx::pack_bf16x2_pinned(r.x, r.y);
     } else {
       hi[e] = ptx::pack_f16x2_pinned(x0, x1);
     }
@@ -135,16 +138,14 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         if (o >= cout) continue;
-        float acc = y[o];
+        float2 acc = make_float2(y[o], 0.f);  // even / odd columns, two FMAs per instruction (fma.f32x2)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 w4 = *reinterpret_cast<const float4*>(w_out_s + o * kTc2H + c0 + q * 4);
-          acc = fmaf(w4.x, hcur[q * 4 + 0], acc);
-          acc = fmaf(w4.y, hcur[q * 4 + 1], acc);
-          acc = fmaf(w4.z, hcur[q * 4 + 2], acc);
-          acc = fmaf(w4.w, hcur[q * 4 + 3], acc);
+          acc = __ffma2_rn(make_float2(w4.x, w4.y), make_float2(hcur[q * 4 + 0], hcur[q * 4 + 1]), acc);
+          acc = __ffma2_rn(make_float2(w4.z, w4.w), make_float2(hcur[q * 4 + 2], hcur[q * 4 + 3]), acc);
         }
-        y[o] = acc;
+        y[o] = acc.x + acc.y;
       }
     }
   }
@@ -586,7 +587,12 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
           tc_unpack_cos16(cpk[2 * c], cpk[2 * c + 1], cs);
           ptx::tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
+          for (int j = 0; j < 16; j += 2) {  // mul.f32x2: two columns per instruction
+            const float2 m = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                        make_float2(cs[j], cs[j + 1]));
+            dl[j] = m.x;
+            dl[j + 1] = m.y;
+          }
           if (l > 1) tc2_store_a16<PREC>(tmem_a, c0, dl);
           if (PACKED) tc_colsum16_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
           else tc_colsum16_to_global(dl, lane, gshift + t * SH + (size_t)(l - 1) * H + c0);

@@ -156,7 +156,8 @@ __device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, uint32_t tmem_row,
       const float x0 = h[2 * e], x1 = h[2 * e + 1];
       if (C::kSplit) {
         hi[e] = ptx::pack_bf16x2(x0, x1);
-        lo[e] = ptx::pack_bf16x2(x0 - ptx::bf16lo_to_f32(hi[e]), x1 - ptx::bf16hi_to_f32(hi[e]));
+        const float2 r = ptx::bf16x2_residual(hi[e], x0, x1);
+        lo[e] = ptx::pack_bf16x2(r.x, r.y);
       } else {
         hi[e] = ptx::pack_f16x2(x0, x1);
       }
@@ -177,7 +178,8 @@ __device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, uint32_t tmem_row,
       const float x0 = h[q * 8 + 2 * e], x1 = h[q * 8 + 2 * e + 1];
       if (C::kSplit) {
         hi[e] = ptx::pack_bf16x2(x0, x1);
-        lo[e] = ptx::pack_bf16x2(x0 - ptx::bf16lo_to_f32(hi[e]), x1 - ptx::bf16hi_to_f32(hi[e]));
+        const float2 r = ptx::bf16x2_residual(hi[e], x0, x1);
+        lo[e] = ptx::pack_bf16x2(r.x, r.y);
       } else {
         hi[e] = ptx::pack_f16x2(x0, x1);
       }
@@ -634,7 +636,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
           tc_unpack_cos16(cpk[2 * c], cpk[2 * c + 1], cs);
           ptx::tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dl[j] = __uint_as_float(v[j]) * cs[j];
+          for (int j = 0; j < 16; j += 2) {  // mul.f32x2: two columns per instruction
+            const float2 m = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                        make_float2(cs[j], cs[j + 1]));
+            dl[j] = m.x;
+            dl[j + 1] = m.y;
+          }
           if (l > 1) tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, dl);
           tc_colsum16_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
         }
