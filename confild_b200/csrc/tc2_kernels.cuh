@@ -45,7 +45,7 @@ __host__ __device__ constexpr size_t tc2_smem_bytes(int num_stages) {
   return 1024 + (size_t)num_stages * kStageBytes + sizeof(Tc2SmemTail);
 }
 
-template <int PREC>
+template <int PREC, bool PACKED_MATH = true>
 __device__ __forceinline__ void tc2_store_a(uint32_t tmem_a, int c0, const float (&h)[32]) {
   constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
   uint32_t hi[16], lo[16];
@@ -54,8 +54,12 @@ __device__ __forceinline__ void tc2_store_a(uint32_t tmem_a, int c0, const float
     const float x0 = h[2 * e], x1 = h[2 * e + 1];
     if (kSplit) {
       hi[e] = ptx::pack_bf16x2(x0, x1);
-      const float2 r = ptx::bf16x2_residual(hi[e], x0, x1);
+      if (PACKED_MATH) {
+        const float2 r = ptx::bf16x2_residual(hi[e], x0, x1);
         lo[e] = ptx::pack_bf16x2(r.x, r.y);
+      } else {
+        lo[e] = ptx::pack_bf16x2(x0 - ptx::bf16lo_to_f32(hi[e]), x1 - ptx::bf16hi_to_f32(hi[e]));
+      }
     } else {
       hi[e] = ptx::pack_f16x2(x0, x1);
     }
@@ -64,8 +68,10 @@ __device__ __forceinline__ void tc2_store_a(uint32_t tmem_a, int c0, const float
   if (kSplit) ptx::tmem_st_32x32b_x16(tmem_a + 64 + c0 / 2, lo);
 }
 
-// 16 activations (columns c0..c0+15 of this thread's row) -> 8 packed words per part -> tcgen05.st.x8
-template <int PREC>
+// 16 activations (columns c0..c0+15 of this thread's row) -> 8 packed words per part -> tcgen05.st.x8.
+// PACKED_MATH: residuals by fma.f32x2 (two columns per instruction); the stash variant of the kernel keeps scalar
+// subtractions (its register pressure turns the 64-bit register pairs into spills: measured 6% slower).
+template <int PREC, bool PACKED_MATH = true>
 __device__ __forceinline__ void tc2_store_a16(uint32_t tmem_a, int c0, const float (&h)[16]) {
   constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
   uint32_t hi[8], lo[8];
@@ -74,9 +80,12 @@ __device__ __forceinline__ void tc2_store_a16(uint32_t tmem_a, int c0, const flo
     const float x0 = h[2 * e], x1 = h[2 * e + 1];
     if (kSplit) {
       hi[e] = ptx::pack_bf16x2_pinned(x0, x1);
-      // residual x - bf16(x) of both columns in one fma.f32x2 (exact: x - h = fma(h, -1, x))
-      const float2 r = ptx::bf16x2_residual(hi[e], x0, x1);
-      lo[e] = ptx::pack_bf16x2_pinned(r.x, r.y);
+      if (PACKED_MATH) {
+        const float2 r = ptx::bf16x2_residual(hi[e], x0, x1);
+        lo[e] = ptx::pack_bf16x2_pinned(r.x, r.y);
+      } else {
+        lo[e] = ptx::pack_bf16x2_pinned(x0 - ptx::bf16lo_to_f32(hi[e]), x1 - ptx::bf16hi_to_f32(hi[e]));
+      }
     } else {
       hi[e] = ptx::pack_f16x2_pinned(x0, x1);
     }
@@ -122,7 +131,7 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
       if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, c + 2), v[c & 1]);
     }
     if (!LAST) {
-      tc2_store_a16<PREC>(tmem_a, c0, hcur);
+      tc2_store_a16<PREC, !STASH>(tmem_a, c0, hcur);
       if (c == 1) {
         ptx::tmem_wait_ld();  // group 3 (the last of D) is in registers
         ptx::tmem_wait_st();
@@ -138,14 +147,27 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         if (o >= cout) continue;
-        float2 acc = make_float2(y[o], 0.f);  // even / odd columns, two FMAs per instruction (fma.f32x2)
+        if (!STASH) {
+          float2 acc = make_float2(y[o], 0.f);  // even / odd columns, two FMAs per instruction (fma.f32x2)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 w4 = *reinterpret_cast<const float4*>(w_out_s + o * kTc2H + c0 + q * 4);
-          acc = __ffma2_rn(make_float2(w4.x, w4.y), make_float2(hcur[q * 4 + 0], hcur[q * 4 + 1]), acc);
-          acc = __ffma2_rn(make_float2(w4.z, w4.w), make_float2(hcur[q * 4 + 2], hcur[q * 4 + 3]), acc);
+          for (int q = 0; q < 4; ++q) {
+            const float4 w4 = *reinterpret_cast<const float4*>(w_out_s + o * kTc2H + c0 + q * 4);
+            acc = __ffma2_rn(make_float2(w4.x, w4.y), make_float2(hcur[q * 4 + 0], hcur[q * 4 + 1]), acc);
+            acc = __ffma2_rn(make_float2(w4.z, w4.w), make_float2(hcur[q * 4 + 2], hcur[q * 4 + 3]), acc);
+          }
+          y[o] = acc.x + acc.y;
+        } else {
+          float acc = y[o];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 w4 = *reinterpret_cast<const float4*>(w_out_s + o * kTc2H + c0 + q * 4);
+            acc = fmaf(w4.x, hcur[q * 4 + 0], acc);
+            acc = fmaf(w4.y, hcur[q * 4 + 1], acc);
+            acc = fmaf(w4.z, hcur[q * 4 + 2], acc);
+            acc = fmaf(w4.w, hcur[q * 4 + 3], acc);
+          }
+          y[o] = acc;
         }
-        y[o] = acc.x + acc.y;
       }
     }
   }
@@ -262,7 +284,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
           h[j] = ptx::sin_approx(r);
           if (STASH) cs0[j] = ptx::cos_approx(r);
         }
-        tc2_store_a<PREC>(tmem_a, c0, h);
+        tc2_store_a<PREC, !STASH>(tmem_a, c0, h);
         if (STASH) {
 #pragma unroll
           for (int q = 0; q < 2; ++q) {

@@ -64,12 +64,19 @@ __device__ __forceinline__ void tc_sines16(const uint32_t (&v)[16], const float*
     const float4 s4 = *reinterpret_cast<const float4*>(sbuf + q * 4);
     const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-    // accumulator + FiLM shift, two columns per instruction (add.f32x2: half the issue slots of scalar FADDs)
-    const float2 z01 = __fadd2_rn(make_float2(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1])),
-                                  make_float2(sv[0], sv[1]));
-    const float2 z23 = __fadd2_rn(make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3])),
-                                  make_float2(sv[2], sv[3]));
-    const float zs[4] = {z01.x, z01.y, z23.x, z23.y};
+    // accumulator + FiLM shift, two columns per instruction (add.f32x2: half the issue slots of scalar FADDs); the
+    // stash variant keeps scalar adds (its register pressure turns the 64-bit pairs into spills: measured 6% slower)
+    float zs[4];
+    if (!STASH) {
+      const float2 z01 = __fadd2_rn(make_float2(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1])),
+                                    make_float2(sv[0], sv[1]));
+      const float2 z23 = __fadd2_rn(make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3])),
+                                    make_float2(sv[2], sv[3]));
+      zs[0] = z01.x; zs[1] = z01.y; zs[2] = z23.x; zs[3] = z23.y;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) zs[e] = __uint_as_float(v[q * 4 + e]) + sv[e];
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float r = REDUCE ? ptx::reduce_2pi(zs[e]) : zs[e];
