@@ -156,17 +156,17 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
             acc = __ffma2_rn(make_float2(w4.z, w4.w), make_float2(hcur[q * 4 + 2], hcur[q * 4 + 3]), acc);
           }
           y[o] = acc.x + acc.y;
-        } else {
-          float acc = y[o];
+        } else {  // scalar FMAs in the same even / odd order: bit-identical to the packed variant
+          float acc_e = y[o], acc_o = 0.f;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 w4 = *reinterpret_cast<const float4*>(w_out_s + o * kTc2H + c0 + q * 4);
-            acc = fmaf(w4.x, hcur[q * 4 + 0], acc);
-            acc = fmaf(w4.y, hcur[q * 4 + 1], acc);
-            acc = fmaf(w4.z, hcur[q * 4 + 2], acc);
-            acc = fmaf(w4.w, hcur[q * 4 + 3], acc);
+            acc_e = fmaf(w4.x, hcur[q * 4 + 0], acc_e);
+            acc_o = fmaf(w4.y, hcur[q * 4 + 1], acc_o);
+            acc_e = fmaf(w4.z, hcur[q * 4 + 2], acc_e);
+            acc_o = fmaf(w4.w, hcur[q * 4 + 3], acc_o);
           }
-          y[o] = acc;
+          y[o] = acc_e + acc_o;
         }
       }
     }

@@ -8,10 +8,10 @@
 //               tcgen05.ld of the fp32 accumulator 16 columns at a time, + FiLM shift, MUFU sin, split into bf16 hi/lo
 //               (or fp16), 16-byte conflict-free st.shared into the next layer's A operand; last layer: partial dot
 //               with the output head, the four column groups meet in shared memory.
-//   warp 16     MMA issuer: the whole warp walks the schedule, one elected lane issues tcgen05.mma (M=128, N=256/128,
-//               K=16) for every (K slab, hi/lo pass, row-block set); accumulators in TMEM.
-//   warp 17     second MMA issuer of the H=256/384 forward kernels (see kHalfOverlap); idle otherwise.
-//   warp 18     one lane streams the pre-swizzled 16 KiB weight stages from L2 with 1-D bulk TMA copies.
+//   warps 16-18 MMA issuers: each whole warp walks the schedule, one elected lane issues tcgen05.mma (M=128, K=16);
+//               accumulators in TMEM.  The forward kernels for H=256/384 use one warp per 128-column accumulator block
+//               (see kBlockPipe); the backward kernels and H=128 use warp 16 only.
+//   warp 19     one lane streams the pre-swizzled 16 KiB weight stages from L2 with 1-D bulk TMA copies.
 // Hand-shakes: b_full/b_empty per ring slot, a_full (A operand written, 512 arrivals), d_full (layer's MMAs done).
 // Sixteen activation warps (four per SM sub-partition) bring the epilogue to the MUFU bound; MMA and epilogue of a tile
 // do not overlap here (a second 128 x H operand does not fit: 2 x 192 KB at H = 384).
@@ -26,7 +26,9 @@
 namespace cnf {
 
 constexpr int kTcEpiWarps = 16;
-constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;
+constexpr int kTcIssuerWarps = 3;
+constexpr int kTcThreads = (kTcEpiWarps + kTcIssuerWarps + 1) * 32;
+constexpr int kTcTailBytes = 384;  // shared-memory area reserved for TcSmemTail
 
 template <int H, int PREC>
 struct TcCfg {
@@ -44,13 +46,13 @@ struct TcCfg {
   static constexpr int kABytes = kParts * kAPartBytes;
   static constexpr int kStagesPerLayer = kNBlocks * kSlabs * kParts;
   static constexpr int kColsPerGroup = H / 4;  // columns per activation column group
-  // Forward overlap (H = 256, 384): column group cg owns columns [64c + 16cg, +16) of every K slab c, i.e. its c-th
-  // 16-column group belongs to K slab c of the next layer's A operand.  After kEarlyGroups groups a thread holds the rest
-  // of its accumulator row in registers (two groups, software pipeline) and arrives on a_half: the first kEarlyGroups K
-  // slabs of the next layer's MMAs then run under the rest of the epilogue (half of it at H=256, a third at H=384).
-  static constexpr bool kHalfOverlap = (H == 256 || H == 384);
-  static constexpr int kGroups = kColsPerGroup / 16;                 // 16-column groups per thread = K slabs
-  static constexpr int kEarlyGroups = kGroups >= 4 ? kGroups - 2 : kGroups;
+  // Forward block pipeline (H = 256, 384; NB = H/128 accumulator blocks = K parts).  A layer's MMAs are issued as NB x NB
+  // quadrants Q(n,k) = accumulator block n (N=128) x K part k (two K slabs = activation columns [128k, 128k+128)), in the
+  // order k-major: Q(0,0) Q(1,0) .. Q(0,1) Q(1,1) ..  Block n is complete after Q(n,NB-1), i.e. BEFORE the blocks after it,
+  // so its epilogue E_n (which writes K part n of the next layer's A operand) runs under the remaining quadrants, and the
+  // next layer's Q'(n,0) may start as soon as part 0 is written and block n is drained -- under E_1.., so that MMA and
+  // epilogue of a single tile overlap almost completely (no second tile fits: TMEM and shared memory are full).
+  static constexpr bool kBlockPipe = (H == 256 || H == 384);
   static constexpr uint32_t kTmemCols = (H + kATmemCols) <= 256 ? 256u : 512u;
   static constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, kStageRows);
   static_assert(kColsPerGroup % 16 == 0, "column groups are processed 16 columns at a time");
@@ -61,14 +63,18 @@ struct TcSmemTail {  // lives after the A operand and the weight ring
   uint64_t b_empty[kTcMaxStages];
   uint64_t a_full;
   uint64_t d_full;
-  uint64_t a_half;   // kHalfOverlap: accumulator drained and the first K slabs of the A operand written
-  uint64_t turn[2];  // kHalfOverlap: issue token passed between the two MMA issuer warps
+  // kBlockPipe (forward, H = 256/384):
+  uint64_t e_done[3];     // K part n of the next A operand written (and accumulator block n drained); 512 arrivals
+  uint64_t d_drained[3];  // accumulator block n is in registers (n >= 1); 512 arrivals
+  uint64_t d_done[3];     // accumulator block n complete: commit of issuer warp n after Q(n, NB-1)
+  uint64_t turn[3];       // issue token passed round-robin between the issuer warps
   uint32_t tmem_base;
 };
 
 template <int H, int PREC>
 __host__ __device__ constexpr size_t tc_smem_bytes(int num_stages) {
-  return 1024 /*alignment slack*/ + (size_t)TcCfg<H, PREC>::kABytes + (size_t)num_stages * kStageBytes + 256 +
+  static_assert(sizeof(TcSmemTail) <= kTcTailBytes, "TcSmemTail outgrew its reserved area");
+  return 1024 /*alignment slack*/ + (size_t)TcCfg<H, PREC>::kABytes + (size_t)num_stages * kStageBytes + kTcTailBytes +
          (TcCfg<H, PREC>::kABytes >= 4 * kTileM * 16 ? 0 : 4 * kTileM * 16);
 }
 
@@ -192,7 +198,7 @@ __device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, uint32_t tmem_row,
 
 // Common prologue: barriers, TMEM allocation.  Returns the TMEM base.
 template <int H, int PREC>
-__device__ __forceinline__ uint32_t tc_setup(TcSmemTail* tail, int num_stages, int warp, uint32_t d_full_count = 1) {
+__device__ __forceinline__ uint32_t tc_setup(TcSmemTail* tail, int num_stages, int warp) {
   using C = TcCfg<H, PREC>;
   if (threadIdx.x == 0) {
     for (int s = 0; s < num_stages; ++s) {
@@ -200,10 +206,13 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmemTail* tail, int num_stages, i
       ptx::mbar_init(&tail->b_empty[s], 1);
     }
     ptx::mbar_init(&tail->a_full, kTcEpiWarps * 32);
-    ptx::mbar_init(&tail->d_full, d_full_count);
-    ptx::mbar_init(&tail->a_half, kTcEpiWarps * 32);
-    ptx::mbar_init(&tail->turn[0], 1);
-    ptx::mbar_init(&tail->turn[1], 1);
+    ptx::mbar_init(&tail->d_full, 1);
+    for (int n = 0; n < 3; ++n) {
+      ptx::mbar_init(&tail->e_done[n], kTcEpiWarps * 32);
+      ptx::mbar_init(&tail->d_drained[n], kTcEpiWarps * 32);
+      ptx::mbar_init(&tail->d_done[n], 1);
+      ptx::mbar_init(&tail->turn[n], 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == kTcEpiWarps) {
@@ -224,65 +233,50 @@ __device__ __forceinline__ void tc_wait_d_full(TcSmemTail* tail, int warp, uint3
   ptx::tc_fence_after();
 }
 
-// ------------------------------------------------------------------ forward overlap (H = 256, 384)
-template <int H>
-__device__ __forceinline__ constexpr int tc_slab_col(int cg, int c) { return 64 * c + 16 * cg; }
-
-// One hidden layer for this thread's row and its column group's 16-column groups (kHalfOverlap), one group per K slab.
-// Software pipeline (TMEM load of group c+2 and sines of group c+1 before the split / pack / store of group c); after
-// group kEarlyGroups-1 the rest of the accumulator row is in registers and the first kEarlyGroups K slabs of the next
-// A operand are written: arrive on a_half, so the issuer may overwrite D with that part of the next layer's MMAs while
-// the last two groups are finished; a_full at the end.
+// ------------------------------------------------------------------ forward block pipeline (H = 256, 384)
+// Epilogue of accumulator block n for this thread's row: its column group's 32 columns [128n + 32cg, +32) = two
+// 16-column groups.  Both groups are loaded at once; for n >= 1 the thread then arrives on d_drained[n] (the issuer may
+// overwrite the block with the next layer's Q'(n,0)); sines, bf16 split, store into K part n of the next A operand,
+// arrive on e_done[n].  LAST: output head instead of the stores, no arrivals.
 template <int H, int PREC, bool REDUCE, bool LAST, bool STASH>
-__device__ __forceinline__ void tc_hidden_layer_overlap(uint8_t* a_smem, uint32_t tmem_row, int row, int cg,
-                                                        const float* __restrict__ shl, const float* __restrict__ w_out,
-                                                        int cout, float (&y)[4], __half* stash_l, TcSmemTail* tail) {
+__device__ __forceinline__ void tc_block_epilogue(int n, uint8_t* a_smem, uint32_t tmem_row, int row, int cg,
+                                                  const float* __restrict__ shl, const float* __restrict__ w_out,
+                                                  int cout, float (&y)[4], __half* stash_l, TcSmemTail* tail) {
   using C = TcCfg<H, PREC>;
-  constexpr int NG = C::kGroups;
-  uint32_t v[2][16];
-  float hcur[16], hnext[16];
-  ptx::tmem_ld_32x32b_x16(tmem_row + tc_slab_col<H>(cg, 0), v[0]);
+  const int c0 = 128 * n + 32 * cg;
+  uint32_t v0[16], v1[16];
+  float h0[16], h1[16];
+  ptx::tmem_ld_32x32b_x16(tmem_row + c0, v0);
+  ptx::tmem_ld_32x32b_x16(tmem_row + c0 + 16, v1);
   ptx::tmem_wait_ld();
-  ptx::tmem_ld_32x32b_x16(tmem_row + tc_slab_col<H>(cg, 1), v[1]);
-  tc_sines16<REDUCE, STASH>(v[0], shl + tc_slab_col<H>(cg, 0), hnext,
-                             STASH ? stash_l + (size_t)tc_slab_col<H>(cg, 0) * kTileM : nullptr);
+  if (!LAST && n > 0) {
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(&tail->d_drained[n]);
+  }
+  tc_sines16<REDUCE, STASH>(v0, shl + c0, h0, STASH ? stash_l + (size_t)c0 * kTileM : nullptr);
+  tc_sines16<REDUCE, STASH>(v1, shl + c0 + 16, h1, STASH ? stash_l + (size_t)(c0 + 16) * kTileM : nullptr);
+  if (!LAST) {
+    tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h0);
+    tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0 + 16, h1);
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before();
+    if (C::kABytes > 0) ptx::fence_proxy_async_smem();
+    ptx::mbar_arrive(&tail->e_done[n]);
+  } else {
 #pragma unroll
-  for (int c = 0; c < NG; ++c) {
-    const int c0 = tc_slab_col<H>(cg, c);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) hcur[j] = hnext[j];
-    if (c + 1 < NG) {
-      const int c1 = tc_slab_col<H>(cg, c + 1);
-      ptx::tmem_wait_ld();
-      tc_sines16<REDUCE, STASH>(v[(c + 1) & 1], shl + c1, hnext, STASH ? stash_l + (size_t)c1 * kTileM : nullptr);
-      if (c + 2 < NG) ptx::tmem_ld_32x32b_x16(tmem_row + tc_slab_col<H>(cg, c + 2), v[c & 1]);
-    }
-    if (!LAST) {
-      tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, hcur);
-      if (c == C::kEarlyGroups - 1) {
-        ptx::tmem_wait_ld();  // the last group of D is in registers
-        ptx::tmem_wait_st();
-        ptx::tc_fence_before();
-        if (C::kABytes > 0) ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&tail->a_half);
-      } else if (c == NG - 1) {
-        ptx::tmem_wait_st();
-        ptx::tc_fence_before();
-        if (C::kABytes > 0) ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&tail->a_full);
-      }
-    } else {
+    for (int g = 0; g < 2; ++g) {
+      const float(&hh)[16] = g == 0 ? h0 : h1;
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         if (o >= cout) continue;
         float acc = y[o];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_out + (size_t)o * H + c0) + q);
-          acc = fmaf(w4.x, hcur[q * 4 + 0], acc);
-          acc = fmaf(w4.y, hcur[q * 4 + 1], acc);
-          acc = fmaf(w4.z, hcur[q * 4 + 2], acc);
-          acc = fmaf(w4.w, hcur[q * 4 + 3], acc);
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_out + (size_t)o * H + c0 + g * 16) + q);
+          acc = fmaf(w4.x, hh[q * 4 + 0], acc);
+          acc = fmaf(w4.y, hh[q * 4 + 1], acc);
+          acc = fmaf(w4.z, hh[q * 4 + 2], acc);
+          acc = fmaf(w4.w, hh[q * 4 + 3], acc);
         }
         y[o] = acc;
       }
@@ -290,35 +284,73 @@ __device__ __forceinline__ void tc_hidden_layer_overlap(uint8_t* a_smem, uint32_
   }
 }
 
-// Issue one part of a hidden layer: issuer warp 0 the first kEarlyGroups K slabs (after a_half), issuer warp 1 the rest
-// (after a_full); each called as a whole converged warp.  `slot`/`phase` point at the layer's first weight group and are
-// advanced past the whole layer.  Order: (layer l, part 0) (l, part 1) (l+1, part 0) ... under the ping-pong token:
-// consecutive parts come from different warps because a warp that has issued MMAs is held until the tensor pipe has
-// taken them.  d_full counts one commit per issuer warp.
+// Issuer warp n: the quadrants Q(n, 0..NB-1) of one hidden layer (accumulator block n, N=128 MMAs), called as a whole
+// converged warp.  The token (turn[]) goes round-robin n -> n+1, which yields the k-major order of kBlockPipe and makes
+// consecutive quadrants come from different warps (a warp that has issued MMAs is held until the tensor pipe has taken
+// them).  All quadrants of block n come from this warp, so its commit after Q(n, NB-1) covers the whole block; E_n
+// additionally relies on the tensor pipe completing MMAs in issue order (the quadrants of other blocks that read K part
+// n were issued earlier).  `stage` counts the weight stages consumed so far by ALL warps (ring position).
 template <int H, int PREC>
-__device__ __forceinline__ void tc_issue_part(int which, uint32_t a_addr, uint32_t ring_addr, uint32_t tmem_d,
-                                              TcSmemTail* tail, int num_stages, int& slot, uint32_t& phase,
-                                              uint32_t& a_phase, uint32_t& turn_phase) {
+__device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t ring_addr, uint32_t tmem_d,
+                                               TcSmemTail* tail, int num_stages, int& slot, uint32_t& phase,
+                                               uint32_t& e_phase, uint32_t& turn_phase) {
   using C = TcCfg<H, PREC>;
-  constexpr int kEarly = C::kEarlyGroups;  // K slabs of part 0
-  auto skip = [&](int slabs) {
-    slot += slabs * C::kParts * C::kNBlocks;
+  constexpr int NB = C::kNBlocks;
+  constexpr int kStagesPerQuad = 2 * C::kParts;  // two K slabs x (hi, lo) weight parts, row block n
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kTileM, 128);
+  auto skip = [&](int quads) {
+    slot += quads * kStagesPerQuad;
     while (slot >= num_stages) { slot -= num_stages; phase ^= 1u; }
   };
-  if (which == 1) skip(kEarly);
-  ptx::mbar_wait(which == 0 ? &tail->a_half : &tail->a_full, a_phase);
-  a_phase ^= 1u;
-  ptx::mbar_wait(&tail->turn[which], turn_phase);
-  turn_phase ^= 1u;
-  ptx::tc_fence_after();
-  tc_issue_slabs<H, PREC>(which == 0 ? 0 : kEarly, which == 0 ? kEarly : C::kSlabs, a_addr, ring_addr, tmem_d, tail,
-                          num_stages, slot, phase);
-  if (ptx::elect_one()) {
-    ptx::umma_commit(&tail->d_full);
-    ptx::mbar_arrive(&tail->turn[which ^ 1]);
+  const uint32_t dcol = tmem_d + n * 128;
+  skip(n);  // quadrants Q(0..n-1, 0) of the other warps
+#pragma unroll 1
+  for (int k = 0; k < NB; ++k) {
+    // operands: K part k of A written; block n drained before its first quadrant overwrites it
+    ptx::mbar_wait(&tail->e_done[k], e_phase);
+    if (k == 0 && n > 0) ptx::mbar_wait(&tail->d_drained[n], e_phase);
+    ptx::mbar_wait(&tail->turn[n], turn_phase);
+    turn_phase ^= 1u;
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int ks = 2 * k + s2;
+      const bool a_in_tmem = ks < 2 * C::kATmemBlocks;
+      const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
+      const int ss = a_in_tmem ? 0 : ks - 2 * C::kATmemBlocks;
+      const uint64_t a_hi = ptx::make_desc_k_sw128(a_addr + ss * (kTileM * 128));
+      const uint64_t a_lo = ptx::make_desc_k_sw128(a_addr + C::kAPartBytes + ss * (kTileM * 128));
+#pragma unroll
+      for (int part = 0; part < C::kParts; ++part) {
+        ptx::mbar_wait(&tail->b_full[slot], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t first = (part == 0) ? (uint32_t)((ks | kk) != 0) : 1u;
+            if (a_in_tmem) {
+              ptx::umma_f16_ts(dcol, at_hi + kk * 8, b + 2 * kk, kIdesc, first);
+              if (C::kSplit && part == 0) ptx::umma_f16_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdesc, 1u);
+            } else {
+              ptx::umma_f16_ss(dcol, a_hi + 2 * kk, b + 2 * kk, kIdesc, first);
+              if (C::kSplit && part == 0) ptx::umma_f16_ss(dcol, a_lo + 2 * kk, b + 2 * kk, kIdesc, 1u);
+            }
+          }
+          ptx::umma_commit(&tail->b_empty[slot]);
+          if (s2 == 1 && part == C::kParts - 1) {
+            if (k == NB - 1) ptx::umma_commit(&tail->d_done[n]);
+            ptx::mbar_arrive(&tail->turn[n + 1 == NB ? 0 : n + 1]);
+          }
+        }
+        __syncwarp();
+        if (++slot >= num_stages) { slot = 0; phase ^= 1u; }
+      }
+    }
+    if (k + 1 < NB) skip(NB - 1);  // the other warps' quadrants of this K part and the start of the next
   }
-  __syncwarp();
-  if (which == 0) skip(C::kSlabs - kEarly);
+  skip(NB - 1 - n);  // quadrants Q(n+1.., NB-1)
+  e_phase ^= 1u;
 }
 
 // ------------------------------------------------------------------ forward
@@ -342,7 +374,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
   const int64_t PB = (P + kTileM - 1) / kTileM;
   const int64_t tiles = tc_num_tiles(T, P, pack_rows);
   const int64_t SH = (int64_t)(nl + 1) * H;
-  const uint32_t tmem_base = tc_setup<H, PREC>(tail, num_stages, warp, C::kHalfOverlap ? 2u : 1u);
+  const uint32_t tmem_base = tc_setup<H, PREC>(tail, num_stages, warp);
 
   if (warp < kTcEpiWarps) {
     // ===================== activation warps =====================
@@ -356,7 +388,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     // [3][128] partial head sums: in the A operand's shared memory when there is one (free after the last layer),
     // else (all of A in TMEM) in a dedicated 6 KiB area behind the barriers
     float4* y_part = C::kABytes >= 4 * kTileM * 16 ? reinterpret_cast<float4*>(a_smem)
-                                                   : reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tail) + 256);
+                                                   : reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tail) + kTcTailBytes);
     uint32_t d_phase = 0;
     CNF_TRACE_DECL;
     const bool tracer = (lane == 0);
@@ -376,9 +408,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
       __half* st_row = STASH ? stash + (size_t)tile * SH * kTileM + row * 8 : nullptr;  // tile-major stash
 
       // ---- layer 0: K = cin on CUDA cores, always range-reduced (|arg| reaches tens of radians)
+      if (C::kBlockPipe) {  // no accumulator to drain before the tile's first MMAs (phases must still advance)
+        ptx::tc_fence_before();
+        for (int n = 1; n < C::kNBlocks; ++n) ptx::mbar_arrive(&tail->d_drained[n]);
+      }
 #pragma unroll 1
       for (int c = 0; c < C::kColsPerGroup / 16; ++c) {
-        const int c0 = C::kHalfOverlap ? tc_slab_col<H>(cg, c) : col_lo + c * 16;
+        // block pipeline: this thread's columns are [128n + 32cg, +32) of every K part n, part 0 first
+        const int c0 = C::kBlockPipe ? 128 * (c / 2) + 32 * cg + 16 * (c & 1) : col_lo + c * 16;
         float h[16];
         [[maybe_unused]] float cs[16];
 #pragma unroll
@@ -393,34 +430,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         }
         tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
         if (STASH) tc_stash16(st_row + (size_t)c0 * kTileM, cs);
-        if (C::kHalfOverlap && c == C::kEarlyGroups - 1) {  // the first K slabs of the A operand are written
+        if (C::kBlockPipe && (c & 1)) {  // K part c/2 of the A operand is written
           ptx::tmem_wait_st();
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&tail->a_half);
+          ptx::mbar_arrive(&tail->e_done[c / 2]);
         }
       }
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&tail->a_full);
+      if (!C::kBlockPipe) {
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&tail->a_full);
+      }
 
       float y[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int l = 1; l <= nl; ++l) {
         const float* shl = sh + (size_t)l * H;
-        tc_wait_d_full(tail, warp, d_phase);
-        if (tracer) CNF_TRACE_EVENT(trole, 300 + l);  // d_full observed
         const bool last = (l == nl);
-        if constexpr (C::kHalfOverlap) {
+        if constexpr (C::kBlockPipe) {
           __half* stl = STASH ? st_row + (size_t)l * H * kTileM : nullptr;
-          if (!last) {
-            tc_hidden_layer_overlap<H, PREC, REDUCE, false, STASH>(a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
-          } else {
-            tc_hidden_layer_overlap<H, PREC, REDUCE, true, STASH>(a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
-            ptx::tc_fence_before();
+#pragma unroll 1
+          for (int n = 0; n < C::kNBlocks; ++n) {
+            // accumulator block n is complete before the blocks after it: its epilogue runs under their MMAs
+            if (warp == 0) ptx::mbar_wait(&tail->d_done[n], d_phase);
+            ptx::bar_sync(1, kTcEpiWarps * 32);
+            ptx::tc_fence_after();
+            if (tracer) CNF_TRACE_EVENT(trole, 300 + 10 * l + n);  // block n observed complete
+            if (!last)
+              tc_block_epilogue<H, PREC, REDUCE, false, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+            else
+              tc_block_epilogue<H, PREC, REDUCE, true, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+            if (tracer) CNF_TRACE_EVENT(trole, 600 + 10 * l + n);  // epilogue of block n done
           }
+          d_phase ^= 1u;
+          if (last) ptx::tc_fence_before();
         } else {
+          tc_wait_d_full(tail, warp, d_phase);
+          if (tracer) CNF_TRACE_EVENT(trole, 300 + l);  // d_full observed
 #pragma unroll 1
           for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
             uint32_t v[16];
@@ -496,7 +544,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
       ptx::bar_sync(1, kTcEpiWarps * 32);  // partial sums consumed before the next tile's layer 0 overwrites them
     }
     ptx::tc_fence_before();
-  } else if (warp < kTcEpiWarps + 2) {
+  } else if (warp < kTcEpiWarps + kTcIssuerWarps) {
     // ===================== MMA issuers (whole warps, one elected lane issues) =====================
     const int which = warp - kTcEpiWarps;
     const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
@@ -504,13 +552,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     int slot = 0;
     uint32_t b_phase = 0, a_phase = 0;
     CNF_TRACE_DECL;
-    if constexpr (C::kHalfOverlap) {
-      // warp `which` issues part `which` of every layer (see tc_issue_part), ordered by a ping-pong token
-      uint32_t turn_phase = which == 0 ? 1u : 0u;  // half 0 first (a fresh barrier passes a parity-1 wait)
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        for (int l = 1; l <= nl; ++l) {
-          tc_issue_part<H, PREC>(which, a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase, turn_phase);
-          if (lane == 0) CNF_TRACE_EVENT(2 + which, 3000 + l);  // this warp's half of the layer issued and committed
+    if constexpr (C::kBlockPipe) {
+      if (which < C::kNBlocks) {  // issuer warp n owns accumulator block n (see tc_issue_block)
+        uint32_t turn_phase = which == 0 ? 1u : 0u;  // block 0 first (a fresh barrier passes a parity-1 wait)
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+          for (int l = 1; l <= nl; ++l) {
+            tc_issue_block<H, PREC>(which, a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase,
+                                    turn_phase);
+            if (lane == 0) CNF_TRACE_EVENT(2 + which, 3000 + l);  // block `which` of layer l issued and committed
+          }
         }
       }
     } else if (which == 0) {
@@ -536,9 +586,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         for (int l = 0; l < nl; ++l) {
           const uint8_t* src = wsrc + (size_t)l * C::kStagesPerLayer * kStageBytes;
           for (int s = 0; s < C::kStagesPerLayer; ++s) {
+            // image order: K slab -> part -> row block.  Block pipeline: consumed quadrant by quadrant, K part k-major
+            // then row block n, then the part's two K slabs, then hi/lo
+            int img = s;
+            if (C::kBlockPipe) {
+              constexpr int NB = C::kNBlocks, kSPQ = 2 * C::kParts;
+              const int q = s / kSPQ, r = s % kSPQ;
+              const int k = q / NB, n = q % NB, ks = 2 * k + r / C::kParts, part = r % C::kParts;
+              img = (ks * C::kParts + part) * NB + n;
+            }
             ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);
             ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kStageBytes);
-            ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
+            ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)img * kStageBytes, kStageBytes,
                           &tail->b_full[slot]);
             if (++slot == num_stages) { slot = 0; phase ^= 1u; }
           }
@@ -655,8 +714,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
         }
       }
     }
-  } else if (warp == kTcEpiWarps + 1) {
-    // second issuer warp: unused by the backward kernel
+  } else if (warp > kTcEpiWarps && warp < kTcEpiWarps + kTcIssuerWarps) {
+    // issuer warps 1, 2: unused by the backward kernel
   } else if (warp == kTcEpiWarps) {
     const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
