@@ -31,11 +31,14 @@ def nth(evs, code, n):
             k += 1
     return None
 TILE = 3
+NB = dims[4] // 128
 prev = None
 for l in (3, 4, 5, 6):
-    r0 = nth(ev[2], 2000 + l, TILE); i0 = nth(ev[2], 3000 + l, TILE)
-    d = [nth(ev[4 + w], 300 + l, TILE) for w in (0, 5, 10, 15)]
-    e = [nth(ev[4 + w], 400 + l, TILE) for w in (0, 5, 10, 15)]
-    print(f"layer {l}: issuer A ready {r0} issued {i0} (+{i0 - r0}) | d_full seen {d[0]} (+{d[0] - i0}) | "
-          f"epilogue done (warps 0,5,10,15) {[x - d[0] for x in e]}" + (f" | layer period {d[0] - prev}" if prev else ""))
-    prev = d[0]
+    parts = []
+    for n in range(NB):
+        d = nth(ev[4], 300 + 10 * l + n, TILE); e = [nth(ev[4 + w], 600 + 10 * l + n, TILE) for w in (0, 5, 10, 15)]
+        parts.append(f"block {n}: complete seen {d}, epilogue done +{[x - d for x in e]}")
+    iss = [nth(ev[2 + n], 3000 + l, TILE) for n in range(NB)]
+    d0 = nth(ev[4], 300 + 10 * l, TILE)
+    print(f"layer {l}: " + " | ".join(parts) + f" | issuers done {iss}" + (f" | period {d0 - prev}" if prev else ""))
+    prev = d0
