@@ -657,8 +657,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
           if (o < cout) gy[o] = gout[(t * P + p) * cout + o];
       }
       // ---- seed: delta at the last sine layer
+      if (C::kBlockPipe) {  // no accumulator to drain before the tile's first MMAs (phases must still advance)
+        ptx::tc_fence_before();
+        for (int n = 1; n < C::kNBlocks; ++n) ptx::mbar_arrive(&tail->d_drained[n]);
+      }
 #pragma unroll 1
-      for (int c0 = col_lo; c0 < col_hi; c0 += 16) {
+      for (int c = 0; c < C::kColsPerGroup / 16; ++c) {
+        // block pipeline: this thread's columns are [128n + 32cg, +32) of every K part n, part 0 first
+        const int c0 = C::kBlockPipe ? 128 * (c / 2) + 32 * cg + 16 * (c & 1) : col_lo + c * 16;
         float cs[16], dl[16];
         tc_load_cos16(st_row + ((size_t)nl * H + c0) * kTileM, cs);
 #pragma unroll
@@ -671,14 +677,68 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
         }
         tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, dl);
         tc_colsum16_rows(dl, lane, t, gshift + (size_t)nl * H + c0, SH);
+        if (C::kBlockPipe && (c & 1)) {  // K part c/2 of the A operand is written
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&tail->e_done[c / 2]);
+        }
       }
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&tail->a_full);
+      if (!C::kBlockPipe) {
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&tail->a_full);
+      }
 
 #pragma unroll 1
       for (int l = nl; l >= 1; --l) {
+        if constexpr (C::kBlockPipe) {
+          // block pipeline (see kBlockPipe): accumulator block n = delta columns [128n, 128n+128) is complete before the
+          // blocks after it; its epilogue (cos multiply, K part n of the next A operand, column sums) runs under their MMAs
+#pragma unroll 1
+          for (int n = 0; n < C::kNBlocks; ++n) {
+            const int c0 = 128 * n + 32 * cg;
+            uint4 cpk[4];  // stashed cos of the layer below for this block's 32 columns: fetched before the wait
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              tc_load_cos_chunk(st_row + ((size_t)(l - 1) * H + c0 + q * 8) * kTileM, cpk[q]);
+            if (warp == 0) ptx::mbar_wait(&tail->d_done[n], d_phase);
+            ptx::bar_sync(1, kTcEpiWarps * 32);
+            ptx::tc_fence_after();
+            uint32_t v0[16], v1[16];
+            ptx::tmem_ld_32x32b_x16(tmem_row + c0, v0);
+            ptx::tmem_ld_32x32b_x16(tmem_row + c0 + 16, v1);
+            ptx::tmem_wait_ld();
+            if (l > 1 && n > 0) {  // block n is in registers: the next layer's Q'(n,0) may overwrite it
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(&tail->d_drained[n]);
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const uint32_t(&v)[16] = g == 0 ? v0 : v1;
+              float cs[16], dl[16];
+              tc_unpack_cos16(cpk[2 * g], cpk[2 * g + 1], cs);
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {  // mul.f32x2: two columns per instruction
+                const float2 m = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                            make_float2(cs[j], cs[j + 1]));
+                dl[j] = m.x;
+                dl[j + 1] = m.y;
+              }
+              if (l > 1) tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0 + 16 * g, dl);
+              tc_colsum16_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0 + 16 * g, SH);
+            }
+            if (l > 1) {
+              ptx::tmem_wait_st();
+              ptx::tc_fence_before();
+              ptx::fence_proxy_async_smem();
+              ptx::mbar_arrive(&tail->e_done[n]);
+            }
+          }
+          d_phase ^= 1u;
+          if (l == 1) ptx::tc_fence_before();
+        } else {
         // prefetch this thread's stashed cos of the layer below (independent of the MMA) before waiting for it
         constexpr int kChunks = C::kColsPerGroup / 8;
         uint4 cpk[kChunks];
@@ -712,21 +772,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
         } else {
           ptx::tc_fence_before();
         }
+        }
       }
     }
-  } else if (warp > kTcEpiWarps && warp < kTcEpiWarps + kTcIssuerWarps) {
-    // issuer warps 1, 2: unused by the backward kernel
-  } else if (warp == kTcEpiWarps) {
+  } else if (warp < kTcEpiWarps + kTcIssuerWarps) {
+    const int which = warp - kTcEpiWarps;
     const uint32_t a_addr = ptx::smem_u32(a_smem), ring_addr = ptx::smem_u32(ring);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int slot = 0;
     uint32_t b_phase = 0, a_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      for (int l = nl; l >= 1; --l) {
-        ptx::mbar_wait(&tail->a_full, a_phase);
-        a_phase ^= 1u;
-        ptx::tc_fence_after();
-        tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
+    if constexpr (C::kBlockPipe) {
+      if (which < C::kNBlocks) {  // issuer warp n owns accumulator block n (see tc_issue_block)
+        uint32_t turn_phase = which == 0 ? 1u : 0u;
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+          for (int l = nl; l >= 1; --l)
+            tc_issue_block<H, PREC>(which, a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase, turn_phase);
+      }
+    } else if (which == 0) {
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int l = nl; l >= 1; --l) {
+          ptx::mbar_wait(&tail->a_full, a_phase);
+          a_phase ^= 1u;
+          ptx::tc_fence_after();
+          tc_issue_layer<H, PREC>(a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase);
+        }
       }
     }
     __syncwarp();
@@ -739,9 +808,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
         for (int l = nl - 1; l >= 0; --l) {
           const uint8_t* src = wsrc + (size_t)l * C::kStagesPerLayer * kStageBytes;
           for (int s = 0; s < C::kStagesPerLayer; ++s) {
+            int img = s;  // block pipeline: quadrant order, see the forward kernel's producer
+            if (C::kBlockPipe) {
+              constexpr int NB = C::kNBlocks, kSPQ = 2 * C::kParts;
+              const int q = s / kSPQ, r = s % kSPQ;
+              const int k = q / NB, n = q % NB, ks = 2 * k + r / C::kParts, part = r % C::kParts;
+              img = (ks * C::kParts + part) * NB + n;
+            }
             ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);
             ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kStageBytes);
-            ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)s * kStageBytes, kStageBytes,
+            ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)img * kStageBytes, kStageBytes,
                           &tail->b_full[slot]);
             if (++slot == num_stages) { slot = 0; phase ^= 1u; }
           }
