@@ -192,8 +192,9 @@ class Affine11:
 
 
 def measure_extra(model, coords, lat, dev, args):
-    """Reported next to the headline (never folded into it): the single-pass fp16 fast mode on the same workload and
-    the DPS step of BASELINE config 4 (forward with stash + backward to the latents, 64 frames x 16,384 points)."""
+    """Reported next to the headline (never folded into it): the single-pass fp16 fast mode on the same workload, the DPS
+    step of BASELINE config 4 (forward with stash + backward to the latents, 64 frames x 16,384 points) for case1 and case4
+    shapes, and a case4 decode (config 3 shapes)."""
     import confild_b200 as cb
     from oracle import cnf_oracle as O
 
@@ -239,6 +240,42 @@ def measure_extra(model, coords, lat, dev, args):
                           "workload": f"{CASE} shapes, {Td} latents x {Pd} points, 1000 random sensors, "
                                       "forward(+cos stash) + loss + backward to dL/dlatent (BASELINE config 4)",
                           "precision": args.precision}
+
+    # ---- case4 (3-D recipe: 15 hidden layers of width 384), the shapes of BASELINE configs 3 and 4, at a bounded size
+    del y_meas, mask, cd, ld
+    dims4 = O.CASE_SHAPES["case4"]
+    m4 = cb.SIRENAutodecoder_film(dims4[0], dims4[1], dims4[2], dims4[3], dims4[4], precision=args.precision)
+    m4.load_state_dict(O.init_params(*dims4, seed=0))
+    m4 = m4.eval().to(dev)
+    T4, P4 = 32, 131072
+    c4, l4 = O.synthetic_inputs(dims4[0], dims4[1], T4, P4)
+    c4, l4 = c4.to(dev)[None], l4.to(dev)
+    with torch.no_grad():
+        ms = timed(lambda: m4(c4, l4[:, None]), 3)
+    flops4 = 2 * (dims4[0] * dims4[4] + dims4[3] * dims4[4] ** 2 + dims4[4] * dims4[2])
+    out["case4_decode"] = {"value": T4 * P4 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                           "workload": f"case4 shapes {dict(zip(('cin', 'L', 'cout', 'nl', 'H'), dims4))}, {T4} frames x {P4} "
+                                       "points, forward only (BASELINE config 3 shapes on one GPU, frames reduced)",
+                           "precision": args.precision,
+                           "algorithmic_tflops": T4 * P4 * flops4 / (ms * 1e-3) / 1e12}
+    Td4, Pd4 = 64, 16384
+    cd4 = c4[:, :Pd4].contiguous()
+    ld4 = torch.cat([l4, l4], dim=0)[:Td4].contiguous()
+    mask4 = torch.zeros(Pd4, 1, device=dev)
+    mask4[torch.randperm(Pd4, device=dev)[:1000]] = 1.0
+    y_meas4 = torch.randn(Td4, Pd4, dims4[2], device=dev) * 0.05
+
+    def dps_step4():
+        l = ld4[:, None].detach().requires_grad_(True)
+        y = m4(cd4, l)
+        loss = torch.linalg.norm((y_meas4 - y) * mask4)
+        torch.autograd.grad(loss, l)
+
+    ms = timed(dps_step4, 3)
+    out["dps_fwd_bwd_case4"] = {"value": Td4 * Pd4 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                                "workload": f"case4 shapes, {Td4} latents x {Pd4} points, 1000 random sensors, forward(+cos "
+                                            "stash) + loss + backward to dL/dlatent (BASELINE config 4)",
+                                "precision": args.precision}
     return out
 
 
