@@ -554,6 +554,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
     const uint32_t tmem_a = lane_base + 128;
     const uint32_t bar_slot = 5 + g;
     uint32_t d_phase = 0;
+    CNF_TRACE_DECL;
+    const bool tracer = (lane == 0);
+    [[maybe_unused]] const int trole = 4 + warp;
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + g;
       if (tile >= tiles) continue;
@@ -596,28 +599,44 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           tc_load_cos_chunk(st_row + ((size_t)(l - 1) * H + col0 + q * 8) * kTileM, cpk[q]);
+        if (tracer) CNF_TRACE_EVENT(trole, 200 + l);  // cos prefetch issued, start waiting for d_full
         if (hf == 0 && wq == 0) ptx::mbar_wait(&tail->d_full[g], d_phase);
         d_phase ^= 1u;
         ptx::bar_sync(bar_slot, 256);
         ptx::tc_fence_after();
+        if (tracer) CNF_TRACE_EVENT(trole, 300 + l);  // d_full observed
+        // two 16-column groups at a time: their loads, multiplies, packs and the 32-column transpose-reduce give the
+        // scheduler independent work (a single group at a time left the warp latency-bound at 0.25 IPC)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int c0 = col0 + c * 16;
-          uint32_t v[16];
-          ptx::tmem_ld_32x32b_x16(lane_base + c0, v);
-          float cs[16], dl[16];
-          tc_unpack_cos16(cpk[2 * c], cpk[2 * c + 1], cs);
+        for (int pr = 0; pr < 2; ++pr) {
+          const int c0 = col0 + pr * 32;
+          uint32_t v0[16], v1[16];
+          ptx::tmem_ld_32x32b_x16(lane_base + c0, v0);
+          ptx::tmem_ld_32x32b_x16(lane_base + c0 + 16, v1);
+          float dl[32];
           ptx::tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {  // mul.f32x2: two columns per instruction
-            const float2 m = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
-                                        make_float2(cs[j], cs[j + 1]));
-            dl[j] = m.x;
-            dl[j + 1] = m.y;
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t(&v)[16] = h == 0 ? v0 : v1;
+            float cs[16];
+            tc_unpack_cos16(cpk[4 * pr + 2 * h], cpk[4 * pr + 2 * h + 1], cs);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {  // mul.f32x2: two columns per instruction
+              const float2 m = __fmul2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                          make_float2(cs[j], cs[j + 1]));
+              dl[16 * h + j] = m.x;
+              dl[16 * h + j + 1] = m.y;
+            }
           }
-          if (l > 1) tc2_store_a16<PREC>(tmem_a, c0, dl);
-          if (PACKED) tc_colsum16_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
-          else tc_colsum16_to_global(dl, lane, gshift + t * SH + (size_t)(l - 1) * H + c0);
+          if (l > 1) {
+            float d0[16], d1[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { d0[j] = dl[j]; d1[j] = dl[16 + j]; }
+            tc2_store_a16<PREC>(tmem_a, c0, d0);
+            tc2_store_a16<PREC>(tmem_a, c0 + 16, d1);
+          }
+          if (PACKED) tc_colsum32_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
+          else tc_colsum32_to_global(dl, lane, gshift + t * SH + (size_t)(l - 1) * H + c0);
         }
         ptx::tc_fence_before();
         if (l > 1) {
@@ -625,6 +644,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
           ptx::tc_fence_before();
           ptx::mbar_arrive(&tail->a_full[g]);
         }
+        if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
       }
     }
     ptx::tc_fence_before();
@@ -638,6 +658,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
     uint32_t turn_phase = g == 0 ? 1u : 0u;
     int slot0 = 0;
     uint32_t ph0 = 0;
+    CNF_TRACE_DECL;
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
       const bool mine = (2 * pair + g < tiles);
       for (int l = nl; l >= 1; --l) {
@@ -651,6 +672,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
           }
           ptx::mbar_wait(&tail->a_full[g], a_phase);
           a_phase ^= 1u;
+          if (lane == 0) CNF_TRACE_EVENT(2 + g, 2000 + l);  // operands ready
         }
         ptx::mbar_wait(&tail->turn[g], turn_phase);
         turn_phase ^= 1u;
@@ -682,6 +704,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
           ptx::mbar_arrive(&tail->turn[g ^ 1]);
         }
         __syncwarp();
+        if (mine && lane == 0) CNF_TRACE_EVENT(2 + g, 3000 + l);  // layer issued + committed
         slot0 += kSPL;
         if (slot0 >= num_stages) { slot0 -= num_stages; ph0 ^= 1u; }
       }

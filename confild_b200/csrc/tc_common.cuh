@@ -162,6 +162,21 @@ __host__ __device__ inline int64_t tc_num_tiles(int64_t T, int64_t P, int packed
 // Column sums of a warp's 32 rows when the rows may belong to different frames (packed tiles): `t_lane` is
 // non-decreasing with the lane.  One frame: the plain transpose-reduce; a few frames: one masked reduce per frame;
 // many frames (tiny P): per-row atomics.  `dst0` = gshift + layer/column offset; frame f's row is dst0 + f*SH.
+// 32 columns at once: five halving rounds (16 + 8 + 4 + 2 + 1 shuffles, the 16 of the first round independent of
+// each other); afterwards lane L holds column L summed over the warp's 32 rows -> one red.global per lane.
+__device__ __forceinline__ void tc_colsum32_to_global(float (&v)[32], int lane, float* dst) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      v[i] = (upper ? v[i + off] : v[i]) + recv;
+    }
+  }
+  atomicAdd(dst + lane, v[0]);
+}
 __device__ __forceinline__ void tc_colsum16_rows(float (&v)[16], int lane, int64_t t_lane, float* dst0, int64_t SH) {
   const int64_t t_lo = __shfl_sync(0xffffffffu, t_lane, 0), t_hi = __shfl_sync(0xffffffffu, t_lane, 31);
   if (t_lo == t_hi) {
@@ -178,6 +193,23 @@ __device__ __forceinline__ void tc_colsum16_rows(float (&v)[16], int lane, int64
     for (int j = 0; j < 16; ++j) atomicAdd(dst0 + t_lane * SH + j, v[j]);
   }
 }
+__device__ __forceinline__ void tc_colsum32_rows(float (&v)[32], int lane, int64_t t_lane, float* dst0, int64_t SH) {
+  const int64_t t_lo = __shfl_sync(0xffffffffu, t_lane, 0), t_hi = __shfl_sync(0xffffffffu, t_lane, 31);
+  if (t_lo == t_hi) {
+    tc_colsum32_to_global(v, lane, dst0 + t_lo * SH);
+  } else if (t_hi - t_lo < 4) {
+    for (int64_t f = t_lo; f <= t_hi; ++f) {
+      float w[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) w[j] = (t_lane == f) ? v[j] : 0.f;
+      tc_colsum32_to_global(w, lane, dst0 + f * SH);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) atomicAdd(dst0 + t_lane * SH + j, v[j]);
+  }
+}
+
 
 // First (frame, point) pair index and number of valid rows of a tile; a tile's valid rows are always a prefix and map
 // to CONSECUTIVE pairs q0, q0+1, ... (frame-aligned tiles stay inside one frame), i.e. to one contiguous range of `out`.
