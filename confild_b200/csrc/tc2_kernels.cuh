@@ -634,16 +634,16 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
             for (int j = 0; j < 16; ++j) { d0[j] = dl[j]; d1[j] = dl[16 + j]; }
             tc2_store_a16<PREC>(tmem_a, c0, d0);
             tc2_store_a16<PREC>(tmem_a, c0 + 16, d1);
+            if (pr == 1) {  // the next layer's operand is complete: release the issuer BEFORE the last column sums
+              ptx::tmem_wait_st();
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(&tail->a_full[g]);
+            }
           }
           if (PACKED) tc_colsum32_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
           else tc_colsum32_to_global(dl, lane, gshift + t * SH + (size_t)(l - 1) * H + c0);
         }
         ptx::tc_fence_before();
-        if (l > 1) {
-          ptx::tmem_wait_st();
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&tail->a_full[g]);
-        }
         if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
       }
     }
