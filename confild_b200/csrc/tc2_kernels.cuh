@@ -527,8 +527,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
       ptx::mbar_init(&tail->b_empty[s], 2);
     }
     for (int g = 0; g < 2; ++g) {
+      ptx::mbar_init(&tail->a_half[g], 256);
       ptx::mbar_init(&tail->a_full[g], 256);
-      ptx::mbar_init(&tail->d_full[g], 1);
+      ptx::mbar_init(&tail->d_full[g], 2);  // one commit per issuer warp (K slab 0, K slab 1)
       ptx::mbar_init(&tail->turn[g], 1);
     }
     ptx::fence_mbar_init();
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
   if (warp < kTc2EpiWarps) {
     const int g = warp / 8, hf = (warp / 4) & 1, wq = warp % 4;
     const int row = wq * 32 + lane;
-    const int col0 = 64 * hf;
+    const int col0 = 32 * hf;  // this warpgroup's columns: [32hf, +32) of K slab 0 and [64 + 32hf, +32) of K slab 1
     const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + g * kTc2SlotCols;
     const uint32_t tmem_a = lane_base + 128;
     const uint32_t bar_slot = 5 + g;
@@ -572,7 +573,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
       }
       // ---- seed: delta at the last sine layer, delta_nl = (gy . W_out) .* cos_nl
 #pragma unroll 1
-      for (int c0 = col0; c0 < col0 + 64; c0 += 16) {
+      for (int c = 0; c < 4; ++c) {
+        const int c0 = col0 + 64 * (c >> 1) + 16 * (c & 1);
         float cs[16], dl[16];
         tc_load_cos16(st_row + ((size_t)nl * H + c0) * kTileM, cs);
 #pragma unroll
@@ -584,12 +586,14 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
           dl[j] = gsum * cs[j];
         }
         tc2_store_a16<PREC>(tmem_a, c0, dl);
+        if (c & 1) {  // K slab c/2 of the first operand is written
+          ptx::tmem_wait_st();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(c == 1 ? &tail->a_half[g] : &tail->a_full[g]);
+        }
         if (PACKED) tc_colsum16_rows(dl, lane, t, gshift + (size_t)nl * H + c0, SH);
         else tc_colsum16_to_global(dl, lane, gshift + t * SH + (size_t)nl * H + c0);
       }
-      ptx::tmem_wait_st();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tail->a_full[g]);
 
 #pragma unroll 1
       for (int l = nl; l >= 1; --l) {
@@ -598,21 +602,24 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
         uint4 cpk[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          tc_load_cos_chunk(st_row + ((size_t)(l - 1) * H + col0 + q * 8) * kTileM, cpk[q]);
+          tc_load_cos_chunk(st_row + ((size_t)(l - 1) * H + col0 + 64 * (q >> 2) + 8 * (q & 3)) * kTileM, cpk[q]);
         if (tracer) CNF_TRACE_EVENT(trole, 200 + l);  // cos prefetch issued, start waiting for d_full
         if (hf == 0 && wq == 0) ptx::mbar_wait(&tail->d_full[g], d_phase);
         d_phase ^= 1u;
         ptx::bar_sync(bar_slot, 256);
         ptx::tc_fence_after();
         if (tracer) CNF_TRACE_EVENT(trole, 300 + l);  // d_full observed
-        // two 16-column groups at a time: their loads, multiplies, packs and the 32-column transpose-reduce give the
-        // scheduler independent work (a single group at a time left the warp latency-bound at 0.25 IPC)
+        // Two pairs of 16-column groups: pair 0 = this warpgroup's 32 columns of K slab 0 of the next operand, pair 1 = of
+        // K slab 1.  Working on a pair at a time gives the scheduler independent work (loads, multiplies, packs, one
+        // 32-column transpose-reduce).  After pair 0 is stored, pair 1's accumulator values are drained into registers
+        // and the thread arrives on a_half: the first half of the next layer's MMAs (which overwrite D) runs under pair
+        // 0's column sums and all of pair 1; a_full is signalled before pair 1's column sums, which the MMAs do not need.
+        uint32_t v0[16], v1[16];
+        ptx::tmem_ld_32x32b_x16(lane_base + col0, v0);
+        ptx::tmem_ld_32x32b_x16(lane_base + col0 + 16, v1);
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
-          const int c0 = col0 + pr * 32;
-          uint32_t v0[16], v1[16];
-          ptx::tmem_ld_32x32b_x16(lane_base + c0, v0);
-          ptx::tmem_ld_32x32b_x16(lane_base + c0 + 16, v1);
+          const int c0 = col0 + 64 * pr;
           float dl[32];
           ptx::tmem_wait_ld();
 #pragma unroll
@@ -634,14 +641,29 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
             for (int j = 0; j < 16; ++j) { d0[j] = dl[j]; d1[j] = dl[16 + j]; }
             tc2_store_a16<PREC>(tmem_a, c0, d0);
             tc2_store_a16<PREC>(tmem_a, c0 + 16, d1);
-            if (pr == 1) {  // the next layer's operand is complete: release the issuer BEFORE the last column sums
-              ptx::tmem_wait_st();
-              ptx::tc_fence_before();
-              ptx::mbar_arrive(&tail->a_full[g]);
-            }
           }
-          if (PACKED) tc_colsum32_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
-          else tc_colsum32_to_global(dl, lane, gshift + t * SH + (size_t)(l - 1) * H + c0);
+          // Packed tiles (sensor-sized shapes, latency-bound, more registers per row) skip the early hand-over: they
+          // drain pair 1 only after pair 0's column sums and signal a_half together with a_full.
+          if (pr == 0 && !PACKED) {  // drain the rest of the accumulator row (pair 1) into the registers pair 0 has vacated
+            ptx::tmem_ld_32x32b_x16(lane_base + col0 + 64, v0);
+            ptx::tmem_ld_32x32b_x16(lane_base + col0 + 64 + 16, v1);
+          }
+          if (l > 1 && (!PACKED || pr == 1)) {
+            if (pr == 0) ptx::tmem_wait_ld();
+            ptx::tmem_wait_st();
+            ptx::tc_fence_before();
+            if (PACKED) ptx::mbar_arrive(&tail->a_half[g]);
+            ptx::mbar_arrive(pr == 0 ? &tail->a_half[g] : &tail->a_full[g]);
+          }
+          if (PACKED) {  // rows of several frames per warp
+            tc_colsum32_rows(dl, lane, t, gshift + (size_t)(l - 1) * H + c0, SH);
+            if (pr == 0) {
+              ptx::tmem_ld_32x32b_x16(lane_base + col0 + 64, v0);
+              ptx::tmem_ld_32x32b_x16(lane_base + col0 + 64 + 16, v1);
+            }
+          } else {
+            tc_colsum32_to_global(dl, lane, gshift + t * SH + (size_t)(l - 1) * H + c0);
+          }
         }
         ptx::tc_fence_before();
         if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
@@ -649,62 +671,68 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
     }
     ptx::tc_fence_before();
   } else if (warp < kMmaWarp + 2) {
-    const int g = warp - kMmaWarp;
+    // MMA issuers, one warp per K slab: same half-layer scheme as tc2_forward_kernel (see there)
+    const int half = warp - kMmaWarp;
+    constexpr int kSPH = kSPL / 2;  // stages per half: hi, lo of one K slab
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t ring_addr = ptx::smem_u32(ring);
-    const uint32_t tmem_d = tmem_u + g * kTc2SlotCols;
-    const uint32_t tmem_a = tmem_d + 128;
-    uint32_t a_phase = 0u;
-    uint32_t turn_phase = g == 0 ? 1u : 0u;
-    int slot0 = 0;
+    uint32_t a_phase[2] = {0u, 0u};
+    uint32_t turn_phase = half == 0 ? 1u : 0u;
+    int slot0 = half * kSPH;
     uint32_t ph0 = 0;
     CNF_TRACE_DECL;
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-      const bool mine = (2 * pair + g < tiles);
       for (int l = nl; l >= 1; --l) {
-        if (mine) {
+        {
           int slot = slot0;
           uint32_t ph = ph0;
 #pragma unroll
-          for (int s = 0; s < kSPL; ++s) {
+          for (int s = 0; s < kSPH; ++s) {
             ptx::mbar_wait(&tail->b_full[slot], ph);
-            if (++slot == num_stages) { slot = 0; ph ^= 1u; }
+            if (++slot >= num_stages) { slot = 0; ph ^= 1u; }
           }
-          ptx::mbar_wait(&tail->a_full[g], a_phase);
-          a_phase ^= 1u;
-          if (lane == 0) CNF_TRACE_EVENT(2 + g, 2000 + l);  // operands ready
         }
-        ptx::mbar_wait(&tail->turn[g], turn_phase);
-        turn_phase ^= 1u;
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          int slot = slot0;
 #pragma unroll
-          for (int s = 0; s < kSPL; ++s) {
-            if (mine) {
-              const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
-              const int ks = s / 2, part = s % 2;
+        for (int g = 0; g < 2; ++g) {
+          const bool mine = (2 * pair + g < tiles);
+          const uint32_t tmem_d = tmem_u + g * kTc2SlotCols;
+          const uint32_t tmem_a = tmem_d + 128;
+          if (mine) {
+            ptx::mbar_wait(half == 0 ? &tail->a_half[g] : &tail->a_full[g], a_phase[g]);
+            a_phase[g] ^= 1u;
+            if (lane == 0) CNF_TRACE_EVENT(2 + half, 2000 + 500 * g + l);  // operands ready
+          }
+          ptx::mbar_wait(&tail->turn[half], turn_phase);
+          turn_phase ^= 1u;
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            int slot = slot0;
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint32_t a_hi = tmem_a + (ks * 4 + kk) * 8;
-                if (part == 0) {
-                  ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (ks | kk) != 0);
-                  ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
-                } else {
-                  ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
+            for (int s = 0; s < kSPH; ++s) {
+              if (mine) {
+                const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint32_t a_hi = tmem_a + (half * 4 + kk) * 8;
+                  if (s == 0) {
+                    ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (uint32_t)((half | kk) != 0));
+                    ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
+                  } else {
+                    ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
+                  }
                 }
+                ptx::umma_commit(&tail->b_empty[slot]);
+              } else {
+                ptx::mbar_arrive(&tail->b_empty[slot]);
               }
-              ptx::umma_commit(&tail->b_empty[slot]);
-            } else {
-              ptx::mbar_arrive(&tail->b_empty[slot]);
+              if (++slot >= num_stages) slot = 0;
             }
-            if (++slot == num_stages) slot = 0;
+            if (mine) ptx::umma_commit(&tail->d_full[g]);
+            ptx::mbar_arrive(&tail->turn[half ^ 1]);
           }
-          if (mine) ptx::umma_commit(&tail->d_full[g]);
-          ptx::mbar_arrive(&tail->turn[g ^ 1]);
+          __syncwarp();
+          if (mine && lane == 0) CNF_TRACE_EVENT(2 + half, 3000 + 500 * g + l);  // this half issued + committed
         }
-        __syncwarp();
-        if (mine && lane == 0) CNF_TRACE_EVENT(2 + g, 3000 + l);  // layer issued + committed
         slot0 += kSPL;
         if (slot0 >= num_stages) { slot0 -= num_stages; ph0 ^= 1u; }
       }

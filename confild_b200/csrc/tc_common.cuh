@@ -210,7 +210,6 @@ __device__ __forceinline__ void tc_colsum32_rows(float (&v)[32], int lane, int64
   }
 }
 
-
 // First (frame, point) pair index and number of valid rows of a tile; a tile's valid rows are always a prefix and map
 // to CONSECUTIVE pairs q0, q0+1, ... (frame-aligned tiles stay inside one frame), i.e. to one contiguous range of `out`.
 __device__ __forceinline__ void tc_tile_range(int64_t tile, int64_t T, int64_t P, int64_t PB, int pack_rows, int64_t& q0,
