@@ -200,7 +200,7 @@ int launch_tc2_backward_t(const cnf_dims& d, const uint8_t* packed, const float*
   if (int rc = make_tc2_plan(di, tiles, &plan)) return rc;
   auto kern = cnf::tc2_backward_kernel<PACKED>;
   CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-  kern<<<(unsigned)plan.grid, cnf::kTc2Threads, plan.smem, st>>>(d, packed, gout, reinterpret_cast<const __half*>(stash),
+  kern<<<(unsigned)plan.grid, cnf::kTc2BwdThreads, plan.smem, st>>>(d, packed, gout, reinterpret_cast<const __half*>(stash),
                                                                  gshift, T, P, plan.stages);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;

@@ -48,28 +48,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Latency-critical waits (the MMA issuers, the warp that watches an accumulator): poll with the non-blocking
-// test_wait instead of try_wait.  try_wait compiles to TRYWAIT + NANOSLEEP.SYNCS, and waking the sleeping warp costs
-// a few hundred cycles per hand-off; the poll costs issue slots of one warp only while it waits.
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
+// Register re-partitioning between warpgroups (4 warps, all of them must execute it): the issuer / producer warpgroup
+// gives registers back, the activation warpgroups take them.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_test_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("cnf: mbarrier poll timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
-    }
-  }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // One lane of the (converged) warp is elected; the same lane every time.  Keeping the surrounding control flow

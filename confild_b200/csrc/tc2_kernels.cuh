@@ -23,7 +23,10 @@ namespace cnf {
 
 constexpr int kTc2H = 128;
 constexpr int kTc2EpiWarps = 16;                       // 2 tile slots x 2 column halves x 4 lane quarters
-constexpr int kTc2Threads = (kTc2EpiWarps + 3) * 32;   // + one MMA issuer warp per tile slot + weight producer warp
+constexpr int kTc2Threads = (kTc2EpiWarps + 4) * 32;   // + two MMA issuer warps + weight producer warp + one idle warp
+                                                       // (the last four form the warpgroup that cedes registers)
+constexpr int kTc2BwdThreads = (kTc2EpiWarps + 3) * 32; // backward: no idle warp, no re-partitioning (it did not pay there)
+constexpr int kTc2EpiRegs = 104, kTc2CtlRegs = 64;  // 4 x 32 x (96-64) released = 16 x 32 x (104-96) taken     // registers per thread after setmaxnreg
 constexpr int kTc2SlotCols = 256;
 
 struct Tc2SmemTail {
@@ -228,6 +231,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
+  if (warp < kTc2EpiWarps) ptx::setmaxnreg_inc<kTc2EpiRegs>();
+  else ptx::setmaxnreg_dec<kTc2CtlRegs>();
 
   if (warp < kTc2EpiWarps) {
     // ===================== activation warpgroups =====================
@@ -462,7 +467,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         if (slot0 >= num_stages) { slot0 -= num_stages; ph0 ^= 1u; }
       }
     }
-  } else {
+  } else if (warp == kMmaWarp + 2) {
     // ===================== weight producer =====================
     if (lane == 0) {
       const uint8_t* wsrc = packed + (kSplit ? lay.tc_fwd_x3 : lay.tc_fwd_h);
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
 // cos of the layer below, reduce the tile's 128 points per column with a 16-shuffle transpose-reduce per 16 columns
 // and add the column sums into gshift with one red.global per (warp, column).
 template <bool PACKED>
-__global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
+__global__ void __launch_bounds__(kTc2BwdThreads, 1) tc2_backward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
                                                                       const float* __restrict__ gout,
                                                                       const __half* __restrict__ stash,
                                                                       float* __restrict__ gshift, int64_t T, int64_t P,
@@ -536,7 +541,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
   }
   {
     const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
-    for (int i = threadIdx.x; i < cout * H; i += kTc2Threads) tail->w_out_s[i] = w_out[i];
+    for (int i = threadIdx.x; i < cout * H; i += kTc2BwdThreads) tail->w_out_s[i] = w_out[i];
   }
   if (warp == kMmaWarp) {
     ptx::tmem_alloc(&tail->tmem_base, 512);
@@ -737,7 +742,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_backward_kernel(cnf_dims d
         if (slot0 >= num_stages) { slot0 -= num_stages; ph0 ^= 1u; }
       }
     }
-  } else {
+  } else if (warp == kMmaWarp + 2) {
     if (lane == 0) {
       const uint8_t* wsrc = packed + lay.tc_bwd_x3;
       int slot = 0;

@@ -63,7 +63,6 @@ __device__ __forceinline__ void tc_sines16(const uint32_t (&v)[16], const float*
   for (int q = 0; q < 4; ++q) {
     const float4 s4 = *reinterpret_cast<const float4*>(sbuf + q * 4);
     const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
     // accumulator + FiLM shift, two columns per instruction (add.f32x2: half the issue slots of scalar FADDs); the
     // stash variant keeps scalar adds (its register pressure turns the 64-bit pairs into spills: measured 6% slower)
     float zs[4];
