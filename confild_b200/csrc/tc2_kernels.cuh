@@ -6,11 +6,13 @@
 //                                                [g*256 + 192, +64)  (lo of the bf16 split)
 // so the MMA reads A from TMEM (tcgen05.mma with a TMEM A operand) and shared memory is left to the
 // weights: a 12-deep ring of 16 KiB stages (three whole layers of bf16 hi/lo) streamed once per tile PAIR.
-//   warps 0-3 / 4-7  activation warpgroup of slot 0 / 1: tcgen05.ld D -> +FiLM shift -> MUFU sin -> bf16 hi/lo
-//                    (or fp16) -> tcgen05.st A; last layer: output head in registers.
-//   warp 8           one thread issues the MMAs, alternating slots: MMA(slot 0, layer l) runs while warpgroup 1
-//                    is still in its epilogue of layer l-1 and vice versa.
-//   warp 9           one thread streams weight stages with cp.async.bulk (1-D TMA).
+//   warps 0-7 / 8-15  activation warps of slot 0 / 1 (2 column halves x 4 TMEM lane quarters each): tcgen05.ld D ->
+//                     +FiLM shift -> MUFU sin -> bf16 hi/lo (or fp16) -> tcgen05.st A; last layer: output head in registers.
+//   warps 16, 17      MMA issuers, one per K slab of the A operand: a layer of a slot goes out as two halves, the first
+//                     under the slot's own epilogue, in the order (slot 0, half 0) (slot 0, half 1) (slot 1, half 0) ...
+//                     so that one slot's epilogue also runs under the other slot's MMAs (see the issuer section).
+//   warp 18           one lane streams weight stages with cp.async.bulk (1-D TMA).
+//   warp 19           idle (forward kernel only): completes the control warpgroup that cedes registers (setmaxnreg).
 // Each weight stage is consumed by slot 0 then slot 1 before it is released (M = 256 rows per byte fetched from L2).
 #pragma once
 #include <cuda_runtime.h>
@@ -26,7 +28,8 @@ constexpr int kTc2EpiWarps = 16;                       // 2 tile slots x 2 colum
 constexpr int kTc2Threads = (kTc2EpiWarps + 4) * 32;   // + two MMA issuer warps + weight producer warp + one idle warp
                                                        // (the last four form the warpgroup that cedes registers)
 constexpr int kTc2BwdThreads = (kTc2EpiWarps + 3) * 32; // backward: no idle warp, no re-partitioning (it did not pay there)
-constexpr int kTc2EpiRegs = 104, kTc2CtlRegs = 64;  // 4 x 32 x (96-64) released = 16 x 32 x (104-96) taken     // registers per thread after setmaxnreg
+// registers per thread after setmaxnreg: the CTA pool only holds what was released, 4 x 32 x (96-64) = 16 x 32 x (104-96)
+constexpr int kTc2EpiRegs = 104, kTc2CtlRegs = 64;
 constexpr int kTc2SlotCols = 256;
 
 struct Tc2SmemTail {
