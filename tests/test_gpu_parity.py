@@ -447,3 +447,24 @@ def test_forward_is_bitwise_reproducible_and_grad_mode_invariant(case, T, P):
             assert torch.equal(m(c, lat.cuda()[:, None]), y0)
     y1 = m(c, lat.cuda()[:, None].requires_grad_(True))
     assert torch.equal(y1.detach(), y0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(2, 16, 3, 1, 128), (2, 16, 3, 2, 128), (3, 8, 2, 1, 256), (2, 8, 4, 2, 384)])
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16"])
+def test_shallow_networks_forward_and_gradient(dims, prec):
+    """nl = 1 / 2: the issue schedules (half-layer, block pipeline) start and end inside one or two hidden layers;
+    odd tile counts leave the second tile slot of the H=128 kernels idle in the last pair."""
+    sd = O.init_params(*dims, seed=3)
+    T, P = 3, 300  # 9 tiles of 128 points
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    gout = torch.randn(T, P, dims[2], generator=torch.Generator().manual_seed(11))
+    want = O.forward(sd, coords[None], lat[:, None])
+    gwant = O.grad_latents_from_gout(sd, coords[None], lat[:, None], gout)
+    m = make_model(dims, sd, prec)
+    l = lat.cuda()[:, None].requires_grad_(True)
+    y = m(coords.cuda()[None], l)
+    (g,) = torch.autograd.grad(y, l, grad_outputs=gout.cuda())
+    torch.cuda.synchronize()
+    assert O.rel_l2(y, want) <= (1e-4 if prec == "bf16x3" else 2e-3)
+    assert O.rel_l2(g, gwant) <= 1e-2
