@@ -48,17 +48,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Register re-partitioning between warpgroups (4 warps, all of them must execute it): the issuer / producer warpgroup
-// gives registers back, the activation warpgroups take them.
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-}
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
-}
-
 // One lane of the (converged) warp is elected; the same lane every time.  Keeping the surrounding control flow
 // warp-uniform lets the compiler hold tcgen05 operands in uniform registers (no per-thread waterfall loop).
 __device__ __forceinline__ bool elect_one() {

@@ -12,7 +12,6 @@
 //                     under the slot's own epilogue, in the order (slot 0, half 0) (slot 0, half 1) (slot 1, half 0) ...
 //                     so that one slot's epilogue also runs under the other slot's MMAs (see the issuer section).
 //   warp 18           one lane streams weight stages with cp.async.bulk (1-D TMA).
-//   warp 19           idle (forward kernel only): completes the control warpgroup that cedes registers (setmaxnreg).
 // Each weight stage is consumed by slot 0 then slot 1 before it is released (M = 256 rows per byte fetched from L2).
 #pragma once
 #include <cuda_runtime.h>
@@ -25,11 +24,10 @@ namespace cnf {
 
 constexpr int kTc2H = 128;
 constexpr int kTc2EpiWarps = 16;                       // 2 tile slots x 2 column halves x 4 lane quarters
-constexpr int kTc2Threads = (kTc2EpiWarps + 4) * 32;   // + two MMA issuer warps + weight producer warp + one idle warp
-                                                       // (the last four form the warpgroup that cedes registers)
-constexpr int kTc2BwdThreads = (kTc2EpiWarps + 3) * 32; // backward: no idle warp, no re-partitioning (it did not pay there)
-// registers per thread after setmaxnreg: the CTA pool only holds what was released, 4 x 32 x (96-64) = 16 x 32 x (104-96)
-constexpr int kTc2EpiRegs = 104, kTc2CtlRegs = 64;
+constexpr int kTc2Threads = (kTc2EpiWarps + 3) * 32;   // + two MMA issuer warps + weight producer warp
+// (A 20th warp plus setmaxnreg re-partitioning -- control warpgroup 96 -> 64 registers, activation warps 96 -> 104; the CTA
+// pool only holds what was released -- removed the stash variant's spills (-2.5 %) but cost the power-capped decode 2 %.)
+constexpr int kTc2BwdThreads = kTc2Threads;
 constexpr int kTc2SlotCols = 256;
 
 struct Tc2SmemTail {
@@ -234,8 +232,6 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
-  if (warp < kTc2EpiWarps) ptx::setmaxnreg_inc<kTc2EpiRegs>();
-  else ptx::setmaxnreg_dec<kTc2CtlRegs>();
 
   if (warp < kTc2EpiWarps) {
     // ===================== activation warpgroups =====================
