@@ -36,7 +36,7 @@ UNIT = "point-frames/s"
 #: (profiles/r01_microbench_mma_ldtm_mufu.txt): 15.98 sin/clk/SM, 4.625 T sin/s at 1.965 GHz
 MUFU_PEAK_SIN_PER_S = 4.625e12
 #: DRAM bytes of one tc2_forward_kernel launch at the bench size from `ncu --set full` (profiles/): read + write
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 769948672  # 13.55 MB read + 756.40 MB written (profiles/r01_ncu_tc2_forward_case1_bf16x3_benchsize_v4.txt)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 771521280  # 14.64 MB read + 756.88 MB written (profiles/r01_ncu_tc2_forward_case1_bf16x3_benchsize_final.txt)
 
 
 def flops_per_pf(cin, L, cout, nl, H):
