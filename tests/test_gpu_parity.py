@@ -468,3 +468,27 @@ def test_shallow_networks_forward_and_gradient(dims, prec):
     torch.cuda.synchronize()
     assert O.rel_l2(y, want) <= (1e-4 if prec == "bf16x3" else 2e-3)
     assert O.rel_l2(g, gwant) <= 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"CNF_TC2": "0"}, {"CNF_TC_STAGES": "8"}, {"CNF_TC_STAGES": "6"}, {"CNF_TC_REDUCE": "1"}])
+@pytest.mark.parametrize("case", ["case1", "case2"])
+def test_debug_knobs_keep_parity(env, case, monkeypatch):
+    """The environment knobs (generic kernel for H=128, shallower weight ring, range reduction in the hidden layers) select
+    other code paths / schedules of the same arithmetic: results stay within the contract, forward and gradient."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    dims = O.CASE_SHAPES[case]
+    sd = O.init_params(*dims, seed=0)
+    T, P = 5, 700
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    gout = torch.randn(T, P, dims[2], generator=torch.Generator().manual_seed(5))
+    want = O.forward(sd, coords[None], lat[:, None])
+    gwant = O.grad_latents_from_gout(sd, coords[None], lat[:, None], gout)
+    m = make_model(dims, sd, "bf16x3")
+    l = lat.cuda()[:, None].requires_grad_(True)
+    y = m(coords.cuda()[None], l)
+    (g,) = torch.autograd.grad(y, l, grad_outputs=gout.cuda())
+    torch.cuda.synchronize()
+    assert O.rel_l2(y, want) <= 1e-4
+    assert O.rel_l2(g, gwant) <= 1e-2
