@@ -64,6 +64,26 @@ def cpu_reference_step(sd, coords, lat):
         return O.forward(sd, coords[None], lat[:, None])
 
 
+CASE4_DIMS = (3, 384, 3, 15, 384)  # the 3-D recipe (BASELINE configs 3 and 4)
+
+
+def synthetic_inputs(cin, L, T, P, sigma=0.1, coord_seed=1, latent_seed=2):
+    """coords ~ U(-1,1) (P,cin), generator seed 1; latents ~ N(0, sigma^2) (T,L), generator seed 2 (SURVEY.md 8(d) 'Inputs').
+    Same draws as the oracle's generator (tests/test_bench_cpu.py checks that), kept here so that the measured arm does not
+    touch oracle/."""
+    gc = torch.Generator().manual_seed(coord_seed)
+    gl = torch.Generator().manual_seed(latent_seed)
+    return torch.rand(P, cin, generator=gc) * 2 - 1, torch.randn(T, L, generator=gl) * sigma
+
+
+def seeded_model(cb, dims, precision):
+    """Random-init weights of the named architecture: the module's own constructor under torch.manual_seed(0) draws them
+    in the reference constructor's order (bit-identical to the reference, tests/test_host.py)."""
+    cin, L, cout, nl, H = dims
+    torch.manual_seed(0)
+    return cb.SIRENAutodecoder_film(cin, L, cout, nl, H, precision=precision)
+
+
 def run_cpu_baseline(sample_frames=16, reps=3):
     """Oracle port of the reference decode (identical op order) on all host cores, bounded sample."""
     from oracle import cnf_oracle as O
@@ -196,7 +216,6 @@ def measure_extra(model, coords, lat, dev, args):
     step of BASELINE config 4 (forward with stash + backward to the latents, 64 frames x 16,384 points) for case1 and case4
     shapes, and a case4 decode (config 3 shapes)."""
     import confild_b200 as cb
-    from oracle import cnf_oracle as O
 
     cin, L, cout, nl, H = DIMS
     T, P = args.frames, args.points
@@ -223,7 +242,7 @@ def measure_extra(model, coords, lat, dev, args):
                                  "note": "single fp16 MMA per product; forward rel-L2 vs reference 3.8e-4 at case1 "
                                          "(inside the 1e-3 contract, outside it for case3/case4)"}
     Td, Pd = 64, 16384
-    cd, ld = O.synthetic_inputs(cin, L, Td, Pd)
+    cd, ld = synthetic_inputs(cin, L, Td, Pd)
     cd, ld = cd.to(dev)[None], ld.to(dev)
     mask = torch.zeros(Pd, 1, device=dev)
     mask[torch.randperm(Pd, device=dev)[:1000]] = 1.0
@@ -243,12 +262,10 @@ def measure_extra(model, coords, lat, dev, args):
 
     # ---- case4 (3-D recipe: 15 hidden layers of width 384), the shapes of BASELINE configs 3 and 4, at a bounded size
     del y_meas, mask, cd, ld
-    dims4 = O.CASE_SHAPES["case4"]
-    m4 = cb.SIRENAutodecoder_film(dims4[0], dims4[1], dims4[2], dims4[3], dims4[4], precision=args.precision)
-    m4.load_state_dict(O.init_params(*dims4, seed=0))
-    m4 = m4.eval().to(dev)
+    dims4 = CASE4_DIMS
+    m4 = seeded_model(cb, dims4, args.precision).eval().to(dev)
     T4, P4 = 32, 131072
-    c4, l4 = O.synthetic_inputs(dims4[0], dims4[1], T4, P4)
+    c4, l4 = synthetic_inputs(dims4[0], dims4[1], T4, P4)
     c4, l4 = c4.to(dev)[None], l4.to(dev)
     with torch.no_grad():
         ms = timed(lambda: m4(c4, l4[:, None]), 3)
@@ -284,7 +301,6 @@ def main_ours(args):
 
     import confild_b200 as cb
     from confild_b200 import _native
-    from oracle import cnf_oracle as O  # parameter / input generators only (seeded, reference constructor order)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -302,11 +318,8 @@ def main_ours(args):
 
     cin, L, cout, nl, H = DIMS
     T, P = args.frames, args.points
-    sd = O.init_params(*DIMS, seed=0)
-    model = cb.SIRENAutodecoder_film(cin, L, cout, nl, H, precision=args.precision)
-    model.load_state_dict(sd)
-    model = model.eval().to(dev)
-    coords_h, lat_h = O.synthetic_inputs(cin, L, T, P, latent_seed=2 + rank)
+    model = seeded_model(cb, DIMS, args.precision).eval().to(dev)
+    coords_h, lat_h = synthetic_inputs(cin, L, T, P, latent_seed=2 + rank)
     coords_h, lat_h = coords_h.pin_memory(), lat_h.pin_memory()
     coords, lat = coords_h.to(dev)[None], lat_h.to(dev)[:, None]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -27,3 +27,27 @@ def test_reference_arm_other_ranks_exit_quietly():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                         "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_measured_arm_generators_match_the_oracle():
+    """bench.py's measured arm builds its weights and inputs without touching oracle/: same draws, bit for bit."""
+    import importlib.util
+
+    import torch
+
+    import confild_b200 as cb
+    from oracle import cnf_oracle as O
+
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.CASE4_DIMS == O.CASE_SHAPES["case4"] and bench.DIMS == O.CASE_SHAPES["case1"]
+    for a, b in zip(bench.synthetic_inputs(2, 128, 5, 77, latent_seed=4), O.synthetic_inputs(2, 128, 5, 77, latent_seed=4)):
+        assert torch.equal(a, b)
+    dims = (2, 16, 3, 2, 32)
+    m = bench.seeded_model(cb, dims, "fp32")
+    want = O.init_params(*dims, seed=0)
+    got = m.state_dict()
+    assert set(got) == set(want)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k

@@ -1,8 +1,8 @@
 """A few plain decode calls of one recipe shape (profiling / A-B timing target):
-    python scripts/decode_once.py case4 16 16384 bf16x3 [check]
+    python tests/tools/decode_once.py case4 16 16384 bf16x3 [check]
 Prints the CUDA-event time per call; with `check`, also the rel-L2 error against the CPU oracle on the first 2 frames."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import confild_b200 as cb
 from oracle import cnf_oracle as O

@@ -1,7 +1,7 @@
 """Times the two halves of a DPS step separately: forward with cos stash, backward to dL/dlatent.
-    python scripts/dps_split.py case1 64 16384"""
+    python tests/tools/dps_split.py case1 64 16384"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import confild_b200 as cb
 from oracle import cnf_oracle as O

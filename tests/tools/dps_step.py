@@ -1,6 +1,6 @@
 """One DPS-style step (forward with stash, sensor loss, backward to latents) for profiling."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import confild_b200 as cb
 from oracle import cnf_oracle as O

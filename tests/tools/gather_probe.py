@@ -1,6 +1,6 @@
 """2+ GPU probe (torchrun): fused all-gather decode vs decode + NCCL all_gather_into_tensor."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
 import confild_b200 as cb

@@ -1,7 +1,7 @@
 """Debug: event trace of CTA 0 of the generic tc_forward_kernel (needs the -DCNF_TRACE build):
-    python scripts/trace_generic.py case4 bf16x3"""
+    python tests/tools/trace_generic.py case4 bf16x3"""
 import ctypes, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 os.environ["CONFILD_CNF_LIB"] = os.path.join(ROOT, "confild_b200", "libconfild_cnf_trace.so")
 import torch
