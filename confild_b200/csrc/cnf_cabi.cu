@@ -113,7 +113,10 @@ int launch_tc_forward(const cnf_dims& d, const uint8_t* packed, const float* coo
   const int64_t tiles = cnf::tc_num_tiles(T, P, pack_rows);
   TcPlan plan;
   if (int rc = make_tc_plan<H, PREC>(di, tiles, &plan)) return rc;
-  auto kern = cnf::tc_forward_kernel<H, PREC, STASH, REDUCE>;
+  // frame-aligned tiles of the block-pipelined kernels stage the layer's FiLM shifts in shared memory
+  constexpr bool kCanStage = cnf::TcCfg<H, PREC>::kBlockPipe;
+  auto kern = (kCanStage && !pack_rows) ? cnf::tc_forward_kernel<H, PREC, STASH, REDUCE, kCanStage>
+                                        : cnf::tc_forward_kernel<H, PREC, STASH, REDUCE, false>;
   CNF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   kern<<<(unsigned)plan.grid, cnf::kTcThreads, plan.smem, st>>>(d, packed, coords, cfs, shift, out,
                                                                 reinterpret_cast<__half*>(stash), T, P, plan.stages, pack_rows);

@@ -75,7 +75,7 @@ template <int H, int PREC>
 __host__ __device__ constexpr size_t tc_smem_bytes(int num_stages) {
   static_assert(sizeof(TcSmemTail) <= kTcTailBytes, "TcSmemTail outgrew its reserved area");
   return 1024 /*alignment slack*/ + (size_t)TcCfg<H, PREC>::kABytes + (size_t)num_stages * kStageBytes + kTcTailBytes +
-         (TcCfg<H, PREC>::kABytes >= 4 * kTileM * 16 ? 0 : 4 * kTileM * 16);
+         (TcCfg<H, PREC>::kABytes >= 4 * kTileM * 16 ? 0 : 4 * kTileM * 16) + (size_t)H * 4 /* staged FiLM shifts */;
 }
 
 // ------------------------------------------------------------------ shared pieces
@@ -354,7 +354,9 @@ __device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t 
 }
 
 // ------------------------------------------------------------------ forward
-template <int H, int PREC, bool STASH, bool REDUCE>
+// STAGE (block pipeline, frame-aligned tiles only): the layer's FiLM shifts are staged in shared memory once per layer
+// instead of being read by every thread with warp-uniform global loads (the H=128 kernel lost 13-20 % without staging).
+template <int H, int PREC, bool STASH, bool REDUCE, bool STAGE = false>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
                                                                    const float* __restrict__ coords,
                                                                    int64_t coord_frame_stride,
@@ -389,6 +391,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     // else (all of A in TMEM) in a dedicated 6 KiB area behind the barriers
     float4* y_part = C::kABytes >= 4 * kTileM * 16 ? reinterpret_cast<float4*>(a_smem)
                                                    : reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(tail) + kTcTailBytes);
+    // one layer of FiLM shifts, behind the barriers and the dedicated head area
+    [[maybe_unused]] float* shift_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tail) + kTcTailBytes +
+                                                               (C::kABytes >= 4 * kTileM * 16 ? 0 : 4 * kTileM * 16));
     uint32_t d_phase = 0;
     CNF_TRACE_DECL;
     const bool tracer = (lane == 0);
@@ -451,6 +456,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         const bool last = (l == nl);
         if constexpr (C::kBlockPipe) {
           __half* stl = STASH ? st_row + (size_t)l * H * kTileM : nullptr;
+          if constexpr (STAGE) {
+            ptx::bar_sync(1, kTcEpiWarps * 32);  // nobody still reads the previous layer's shifts
+            for (int i = threadIdx.x; i < H; i += kTcEpiWarps * 32) shift_s[i] = __ldg(shl + i);
+            // the barrier after the wait on d_done[0] orders these stores before the first read
+          }
 #pragma unroll 1
           for (int n = 0; n < C::kNBlocks; ++n) {
             // accumulator block n is complete before the blocks after it: its epilogue runs under their MMAs
@@ -458,10 +468,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
             ptx::bar_sync(1, kTcEpiWarps * 32);
             ptx::tc_fence_after();
             if (tracer) CNF_TRACE_EVENT(trole, 300 + 10 * l + n);  // block n observed complete
-            if (!last)
-              tc_block_epilogue<H, PREC, REDUCE, false, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
-            else
-              tc_block_epilogue<H, PREC, REDUCE, true, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+            // two call sites per variant so that each sees a pointer of known address space (ld.shared vs ld.global)
+            if constexpr (STAGE) {
+              if (!last)
+                tc_block_epilogue<H, PREC, REDUCE, false, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail);
+              else
+                tc_block_epilogue<H, PREC, REDUCE, true, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail);
+            } else {
+              if (!last)
+                tc_block_epilogue<H, PREC, REDUCE, false, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+              else
+                tc_block_epilogue<H, PREC, REDUCE, true, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+            }
             if (tracer) CNF_TRACE_EVENT(trole, 600 + 10 * l + n);  // epilogue of block n done
           }
           d_phase ^= 1u;
