@@ -2,13 +2,15 @@
 """Headline benchmark: CNF decode throughput in field-points x frames per second.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference ...                      # the reference algorithm on the host cores
+    python bench.py --impl reference ...                      # the reference's own decoder on the host cores
 
 Workload (BASELINE.json configs[1]): case1 shapes (cin,L,H,nl,cout) = (2,128,128,10,3), 1024 frames x
 65,536 query points per GPU, forward only, random-init weights (reference constructor order, seed 0),
 synthetic coords ~ U(-1,1) and latents ~ N(0,0.1^2).  A step = one decode of all frames of the rank
 (FiLM-shift GEMM + fused layer-chain kernel); for N > 1 every rank decodes its own 1024 frames (weak
-scaling) and the decoded field is all-gathered over NCCL inside the step.
+scaling) and the decoded field is all-gathered inside the step (fused into the kernel's epilogue).
+`extra.config3_case4_sharded` is BASELINE.json configs[2]: case4 shapes, 4,096 frames x 131,072 points
+in total, frames sharded over the N ranks (strong scaling), gather inside the step.
 Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement").
 """
 from __future__ import annotations
@@ -29,14 +31,19 @@ import torch  # noqa: E402
 
 CASE = "case1"
 DIMS = (2, 128, 3, 10, 128)  # cin, L, cout, nl, H (oracle order)
+CASE4_DIMS = (3, 384, 3, 15, 384)  # the 3-D recipe (BASELINE configs 3 and 4)
 FRAMES, POINTS = 1024, 65536
+CONFIG3_FRAMES, CONFIG3_POINTS = 4096, 131072
 METRIC = "cnf_decode_point_frames_per_s"
 UNIT = "point-frames/s"
 #: chip-wide sin.approx (MUFU.SIN) throughput measured on this pool's B200 with scripts/microbench.cu
 #: (profiles/r01_microbench_mma_ldtm_mufu.txt): 15.98 sin/clk/SM, 4.625 T sin/s at 1.965 GHz
 MUFU_PEAK_SIN_PER_S = 4.625e12
-#: DRAM bytes of one tc2_forward_kernel launch at the bench size from `ncu --set full` (profiles/): read + write
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 771521280  # 14.64 MB read + 756.88 MB written (profiles/r01_ncu_tc2_forward_case1_bf16x3_benchsize_final.txt)
+#: DRAM bytes (read + write) of ONE launch of the headline kernel at the bench size, from an offline `ncu --set full`
+#: capture of this command (not measured inside this run): {precision: (bytes, profile file)}
+NCU_TRAFFIC_OFFLINE = {
+    "bf16x3": (771521280, "profiles/r01_ncu_tc2_forward_case1_bf16x3_benchsize_final.txt"),
+}
 
 
 def flops_per_pf(cin, L, cout, nl, H):
@@ -56,15 +63,67 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def roofline_block(dims, T, P, kernel_ms, peaks, peak_src, precision, kernel):
+    """Both candidate ceilings of SURVEY.md 8(d) -- algorithmic FLOPs against the measured sustained bf16 tensor
+    peak, algorithmic sines against the measured MUFU peak -- and the rule that names the binding one:
+    bound = argmax(F_alg / P_tensor, S_alg / P_mufu), i.e. the resource whose ideal time is longer."""
+    fl = flops_per_pf(*dims) * T * P
+    sn = sins_per_pf(*dims) * T * P
+    ach_tf = fl / (kernel_ms * 1e-3) / 1e12
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    sin_rate = sn / (kernel_ms * 1e-3)
+    t_tensor, t_mufu = fl / (peak_tf * 1e12), sn / MUFU_PEAK_SIN_PER_S
+    binding = "tensor" if t_tensor >= t_mufu else "mufu"
+    tensor_frac, mufu_frac = ach_tf / peak_tf, sin_rate / MUFU_PEAK_SIN_PER_S
+    traffic, traffic_src = NCU_TRAFFIC_OFFLINE.get(precision, (None, None)) if (T, P) == (FRAMES, POINTS) and dims == DIMS \
+        else (None, None)
+    return {
+        "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tensor_frac,
+        "traffic": traffic, "traffic_source": ("ncu --set full, offline capture, not measured in this run: " + traffic_src)
+        if traffic_src else None,
+        "kernel": kernel, "kernel_ms": kernel_ms, "peak_source": f"{peak_src} bf16_tflops_sustained",
+        "algorithmic_flops_per_launch": fl, "algorithmic_sines_per_launch": sn,
+        "tensor_frac": tensor_frac, "mufu_frac": mufu_frac, "binding": binding,
+        "binding_frac": tensor_frac if binding == "tensor" else mufu_frac,
+        "binding_rule": "argmax(F_alg/P_tensor, S_alg/P_mufu): ideal tensor time %.3f ms vs ideal MUFU time %.3f ms per "
+                        "launch" % (t_tensor * 1e3, t_mufu * 1e3),
+        "mufu": {"achieved_gsin_s": sin_rate / 1e9, "measured_peak_gsin_s": MUFU_PEAK_SIN_PER_S / 1e9, "frac": mufu_frac},
+    }
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_step(sd, coords, lat):
-    from oracle import cnf_oracle as O  # the one place bench.py executes the oracle
+def reference_decoder(dims):
+    """(decode(coords (P,cin), latents (T,L)) -> (T,P,cout), kind, description) on the host.
 
-    with torch.no_grad():
-        return O.forward(sd, coords[None], lat[:, None])
+    kind "reference": the reference's OWN SIRENAutodecoder_film (byte-compiled from /root/reference by
+    oracle/build_ref.py into oracle/_ref, which travels to the GPU box); kind "port": the restated oracle, when
+    oracle/_ref was never built.  Same seed-0 constructor weights either way (bit-identical, tests/test_oracle.py)."""
+    cin, L, cout, nl, H = dims
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import build_ref  # the one other place bench.py executes oracle/
 
+        Ref = build_ref.load_reference_class()
+    except Exception:  # noqa: BLE001
+        Ref = None
+    if Ref is not None:
+        torch.manual_seed(0)
+        model = Ref(cin, L, cout, nl, H).eval()
 
-CASE4_DIMS = (3, 384, 3, 15, 384)  # the 3-D recipe (BASELINE configs 3 and 4)
+        def decode(coords, lat):
+            with torch.no_grad():
+                return model(coords[None], lat[:, None])
+
+        return decode, "reference", "reference SIRENAutodecoder_film.forward (oracle/_ref bytecode of cnf/nf_networks.py)"
+    from oracle import cnf_oracle as O
+
+    sd = O.init_params(*dims, seed=0)
+
+    def decode_port(coords, lat):
+        with torch.no_grad():
+            return O.forward(sd, coords[None], lat[:, None])
+
+    return decode_port, "port", "oracle/cnf_oracle.py restatement (oracle/_ref not built)"
 
 
 def synthetic_inputs(cin, L, T, P, sigma=0.1, coord_seed=1, latent_seed=2):
@@ -85,36 +144,32 @@ def seeded_model(cb, dims, precision):
 
 
 def run_cpu_baseline(sample_frames=16, reps=3):
-    """Oracle port of the reference decode (identical op order) on all host cores, bounded sample."""
-    from oracle import cnf_oracle as O
-
+    """The reference decode on all host cores, bounded sample of the headline workload."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = O.init_params(*DIMS, seed=0)
-    coords, lat = O.synthetic_inputs(DIMS[0], DIMS[1], sample_frames, POINTS)
-    cpu_reference_step(sd, coords, lat[:1])  # warm-up
+    decode, kind, what = reference_decoder(DIMS)
+    coords, lat = synthetic_inputs(DIMS[0], DIMS[1], sample_frames, POINTS)
+    decode(coords, lat[:1])  # warm-up
     best = float("inf")
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_reference_step(sd, coords, lat)
+        decode(coords, lat)
         best = min(best, time.perf_counter() - t0)
-    return {"value": sample_frames * POINTS / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{CASE} shapes, {sample_frames} frames x {POINTS} points, fp32, torch {torch.__version__} CPU, "
-                      f"best of {reps} after warm-up ({best:.2f} s)"}
+    return {"value": sample_frames * POINTS / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{CASE} shapes, {sample_frames} frames x {POINTS} points, fp32, {what}, torch {torch.__version__} "
+                      f"CPU, best of {reps} after warm-up ({best:.2f} s)"}
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import cnf_oracle as O
-
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = O.init_params(*DIMS, seed=0)
-    coords, lat_all = O.synthetic_inputs(DIMS[0], DIMS[1], 16, POINTS)
+    decode, kind, what = reference_decoder(DIMS)
+    coords, lat_all = synthetic_inputs(DIMS[0], DIMS[1], 16, POINTS)
     t0 = time.perf_counter()
-    cpu_reference_step(sd, coords, lat_all[:1])
+    decode(coords, lat_all[:1])
     t1 = time.perf_counter() - t0
     budget = 150.0 / max(1, args.steps + args.warmup)
     sample = 16
@@ -122,20 +177,20 @@ def main_reference(args):
         sample //= 2
     lat = lat_all[:sample]
     for _ in range(args.warmup):
-        cpu_reference_step(sd, coords, lat)
+        decode(coords, lat)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(sd, coords, lat)
+        decode(coords, lat)
     dt = time.perf_counter() - t0
     value = args.steps * sample * POINTS / dt
-    sample_txt = f"{CASE} shapes, {sample} frames x {POINTS} points per step, fp32, all host threads"
+    sample_txt = f"{CASE} shapes, {sample} frames x {POINTS} points per step, fp32, all host threads, {what}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"CNF decode {CASE} 2D shapes, forward only (CPU: bounded sample of the 1024-frame job)",
                    "frames_per_step": sample, "points": POINTS, "dims": dict(zip(("cin", "L", "cout", "nl", "H"), DIMS))},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -198,6 +253,7 @@ class ClockSampler:
 
 class Affine11:
     """'-11' normaliser of the reference (cnf/utils/normalize.py:100-120) with fixed (max, min)."""
+    method = "-11"
 
     def __init__(self, hi, lo):
         self.params = (hi, lo)
@@ -211,89 +267,211 @@ class Affine11:
         return (y + 1) / 2 * (hi - lo) + lo
 
 
+def timed(fn, iters):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def eager_decode(params, coords, lat, w0=30.0):
+    """The reference's forward as plain PyTorch eager ops on the GPU (nf_networks.py:491-494: matmul, in-place bias
+    add, broadcast add, mul, sin per layer) -- the 'PyTorch-eager on the same B200' comparator of SURVEY.md 2.1."""
+    net1, net2 = params
+    x = coords
+    for i in range(len(net2)):
+        w, b = net1[i]
+        h = torch.matmul(x, w.t())
+        h += b
+        x = torch.sin(w0 * (h + torch.matmul(lat, net2[i].t())))
+    w, b = net1[-1]
+    return torch.matmul(x, w.t()) + b
+
+
+def measure_eager(model, dev):
+    nl = model._dims_tuple[3]
+    net1 = [(model.net1[i].weight.detach(), model.net1[i].bias.detach()) for i in range(nl + 2)]
+    net2 = [model.net2[i].weight.detach() for i in range(nl + 1)]
+    T, P = 64, POINTS
+    c, l = synthetic_inputs(DIMS[0], DIMS[1], T, P)
+    c, l = c.to(dev)[None], l.to(dev)[:, None]
+    out = {"workload": f"{CASE} shapes, {T} frames x {P} points, forward only, torch {torch.__version__} eager on the same GPU"}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                ms = timed(lambda: eager_decode((net1, net2), c, l), 3)
+            out[name] = {"value": T * P / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
+
+
+def measure_dps(cb, model, dims, case, dev, args, iters):
+    """BASELINE config 4: 64 latents x 16,384 points, 1,000 random sensors.  Three ways, never folded into the headline:
+    (a) the reference's formulation through the drop-in module and PyTorch autograd (dense dL/dy);
+    (b) the fused measurement norm (cnf_forward_loss, no element-wise PyTorch pass), still dense over all P;
+    (c) sensor-compacted: decode + backward on the 1,000 sensor rows only (what Case3/4Operator do by passing sensor coords)."""
+    cin, L, cout, nl, H = dims
+    Td, Pd, S = 64, 16384, 1000
+    cd, ld = synthetic_inputs(cin, L, Td, Pd)
+    cd, ld = cd.to(dev), ld.to(dev)
+    mask = torch.zeros(Pd, device=dev)
+    mask[torch.randperm(Pd, device=dev)[:S]] = 1.0
+    y_meas = torch.randn(Td, Pd, cout, device=dev) * 0.05
+    ym_masked = y_meas * mask[None, :, None]
+
+    def autograd_step():
+        l = ld[:, None].detach().requires_grad_(True)
+        y = model(cd[None], l)
+        loss = torch.linalg.norm((y_meas - y) * mask[None, :, None])  # condition_methods.py:30-31
+        torch.autograd.grad(loss, l)                                   # condition_methods.py:32
+
+    def fused_step():
+        l = ld[:, None].detach().requires_grad_(True)
+        norm = cb.measurement_norm(model, cd[None], l, ym_masked, mask=mask)
+        torch.autograd.grad(norm, l)
+
+    cs, _, ys = cb.sensor_rows(cd, mask, y_meas)
+
+    def compact_step():
+        l = ld[:, None].detach().requires_grad_(True)
+        norm = cb.measurement_norm(model, cs[None], l, ys)
+        torch.autograd.grad(norm, l)
+
+    res = {"workload": f"{case} shapes, {Td} latents x {Pd} points, {S} random sensors, forward(+cos stash) + loss + "
+                       "backward to dL/dlatent (BASELINE config 4)", "precision": model.precision}
+    for name, fn, rows in (("autograd_dense", autograd_step, Td * Pd), ("fused_loss_dense", fused_step, Td * Pd),
+                           ("sensor_compacted", compact_step, Td * S)):
+        ms = timed(fn, iters)
+        res[name] = {"ms_per_step": ms, "point_frames_per_s": rows / (ms * 1e-3), "rows_per_step": rows}
+    res["value"] = res["fused_loss_dense"]["point_frames_per_s"]
+    res["ms_per_step"] = res["fused_loss_dense"]["ms_per_step"]
+    res["unit"] = UNIT
+    res["note"] = ("value = fused_loss_dense (dense evaluation over all P, the graded quantity); sensor_compacted decodes "
+                   "only the sensor rows and is reported separately (SURVEY.md 8d)")
+    return res
+
+
 def measure_extra(model, coords, lat, dev, args):
-    """Reported next to the headline (never folded into it): the single-pass fp16 fast mode on the same workload, the DPS
-    step of BASELINE config 4 (forward with stash + backward to the latents, 64 frames x 16,384 points) for case1 and case4
-    shapes, and a case4 decode (config 3 shapes)."""
+    """Reported next to the headline (never folded into it): the other precisions on the same workload, the DPS step of
+    BASELINE config 4 for case1 and case4 shapes, the notebook's literal DPS shape, a bounded case4 decode and the
+    PyTorch-eager comparator on the same GPU."""
     import confild_b200 as cb
 
     cin, L, cout, nl, H = DIMS
     T, P = args.frames, args.points
     out = {}
-
-    def timed(fn, iters):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters
-
-    if args.precision != "fp16":
-        fast = cb.SIRENAutodecoder_film(cin, L, cout, nl, H, precision="fp16")
-        fast.load_state_dict(model.state_dict())
-        fast = fast.eval().to(dev)
+    for prec in ("bf16x3", "fp16"):
+        if prec == args.precision:
+            continue
+        other = cb.SIRENAutodecoder_film(cin, L, cout, nl, H, precision=prec)
+        other.load_state_dict(model.state_dict())
+        other = other.eval().to(dev)
         with torch.no_grad():
-            ms = timed(lambda: fast(coords, lat), 3)
-        out["fast_mode_fp16"] = {"value": T * P / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-                                 "note": "single fp16 MMA per product; forward rel-L2 vs reference 3.8e-4 at case1 "
-                                         "(inside the 1e-3 contract, outside it for case3/case4)"}
-    Td, Pd = 64, 16384
-    cd, ld = synthetic_inputs(cin, L, Td, Pd)
-    cd, ld = cd.to(dev)[None], ld.to(dev)
-    mask = torch.zeros(Pd, 1, device=dev)
-    mask[torch.randperm(Pd, device=dev)[:1000]] = 1.0
-    y_meas = torch.randn(Td, Pd, cout, device=dev) * 0.05
+            ms = timed(lambda: other(coords, lat), 3)
+        out[f"precision_{prec}"] = {"value": T * P / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms}
+        del other
+    model.disable_gradient()
+    out["dps_fwd_bwd"] = measure_dps(cb, model, DIMS, CASE, dev, args, 5)
+    out["eager_b200"] = measure_eager(model, dev)
 
-    def dps_step():
-        l = ld[:, None].detach().requires_grad_(True)
-        y = model(cd, l)
-        loss = torch.linalg.norm((y_meas - y) * mask)  # condition_methods.py:30-31
-        torch.autograd.grad(loss, l)                    # condition_methods.py:32
-
-    ms = timed(dps_step, 5)
-    out["dps_fwd_bwd"] = {"value": Td * Pd / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-                          "workload": f"{CASE} shapes, {Td} latents x {Pd} points, 1000 random sensors, "
-                                      "forward(+cos stash) + loss + backward to dL/dlatent (BASELINE config 4)",
-                          "precision": args.precision}
-
-    # ---- case4 (3-D recipe: 15 hidden layers of width 384), the shapes of BASELINE configs 3 and 4, at a bounded size
-    del y_meas, mask, cd, ld
+    # ---- case4 (3-D recipe: 15 hidden layers of width 384), the shapes of BASELINE configs 3 and 4
     dims4 = CASE4_DIMS
     m4 = seeded_model(cb, dims4, args.precision).eval().to(dev)
-    T4, P4 = 32, 131072
-    c4, l4 = synthetic_inputs(dims4[0], dims4[1], T4, P4)
-    c4, l4 = c4.to(dev)[None], l4.to(dev)
-    with torch.no_grad():
-        ms = timed(lambda: m4(c4, l4[:, None]), 3)
-    flops4 = 2 * (dims4[0] * dims4[4] + dims4[3] * dims4[4] ** 2 + dims4[4] * dims4[2])
-    out["case4_decode"] = {"value": T4 * P4 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-                           "workload": f"case4 shapes {dict(zip(('cin', 'L', 'cout', 'nl', 'H'), dims4))}, {T4} frames x {P4} "
-                                       "points, forward only (BASELINE config 3 shapes on one GPU, frames reduced)",
-                           "precision": args.precision,
-                           "algorithmic_tflops": T4 * P4 * flops4 / (ms * 1e-3) / 1e12}
-    Td4, Pd4 = 64, 16384
-    cd4 = c4[:, :Pd4].contiguous()
-    ld4 = torch.cat([l4, l4], dim=0)[:Td4].contiguous()
-    mask4 = torch.zeros(Pd4, 1, device=dev)
-    mask4[torch.randperm(Pd4, device=dev)[:1000]] = 1.0
-    y_meas4 = torch.randn(Td4, Pd4, dims4[2], device=dev) * 0.05
+    m4.disable_gradient()
+    out["dps_fwd_bwd_case4"] = measure_dps(cb, m4, dims4, "case4", dev, args, 3)
+    # the notebook's literal shape: 384 frames x 10 sensor points (ipynb :194-200, :304-306)
+    Tn, Pn = 384, 10
+    cn, ln = synthetic_inputs(dims4[0], dims4[1], Tn, Pn)
+    cn, ln = cn.to(dev), ln.to(dev)
+    ymn = torch.randn(Tn, Pn, dims4[2], device=dev) * 0.05
 
-    def dps_step4():
-        l = ld4[:, None].detach().requires_grad_(True)
-        y = m4(cd4, l)
-        loss = torch.linalg.norm((y_meas4 - y) * mask4)
-        torch.autograd.grad(loss, l)
+    def nb_autograd():
+        l = ln[:, None].detach().requires_grad_(True)
+        torch.autograd.grad(torch.linalg.norm(ymn - m4(cn[None], l)), l)
 
-    ms = timed(dps_step4, 3)
-    out["dps_fwd_bwd_case4"] = {"value": Td4 * Pd4 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-                                "workload": f"case4 shapes, {Td4} latents x {Pd4} points, 1000 random sensors, forward(+cos "
-                                            "stash) + loss + backward to dL/dlatent (BASELINE config 4)",
-                                "precision": args.precision}
+    def nb_fused():
+        l = ln[:, None].detach().requires_grad_(True)
+        torch.autograd.grad(cb.measurement_norm(m4, cn[None], l, ymn), l)
+
+    out["dps_notebook_shape_case4"] = {
+        "workload": f"case4 shapes, {Tn} frames x {Pn} sensor points (the notebook's literal DPS shape), eager launches",
+        "autograd_ms": timed(nb_autograd, 10), "fused_loss_ms": timed(nb_fused, 10)}
     return out
+
+
+def measure_config3(cb, dev, world, rank, args):
+    """BASELINE.json configs[2]: case4 shapes, 4,096 frames x 131,072 points in total, frames sharded over the ranks
+    (strong scaling), decoded field gathered to every rank inside the step (fused into the kernel's epilogue for N > 1).
+    Device-timed, max over ranks."""
+    import torch.distributed as dist
+
+    dims4 = CASE4_DIMS
+    T_total, P = args.config3_frames, CONFIG3_POINTS
+    if T_total % world:
+        return {"skipped": f"{T_total} frames do not split evenly over {world} ranks"}
+    T = T_total // world
+    m4 = seeded_model(cb, dims4, args.precision).eval().to(dev)
+    ev = []
+    m4._timing = ev
+    c4, l4 = synthetic_inputs(dims4[0], dims4[1], T_total, P)
+    c4, l4 = c4.to(dev)[None], l4[rank * T:(rank + 1) * T].to(dev)[:, None]
+    fused = None
+    mode = "single GPU, no gather"
+    if world > 1:
+        fused = cb.FusedGatherDecoder(m4, T, P)
+        mode = "all-gather fused into the decode kernel (peer stores over NVLink, double-buffered symmetric memory)"
+
+    def step():
+        with torch.no_grad():
+            return fused(c4, l4) if fused is not None else m4(c4, l4)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    step()
+    barrier()
+    ev.clear()
+    steps = args.config3_steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms_local = e0.elapsed_time(e1) / steps
+    kern_ms = sum(a.elapsed_time(b) for a, b in ev) / max(1, len(ev))
+    t = torch.tensor([ms_local, kern_ms], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        allms = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allms, t)
+        per_rank = [float(x[0]) for x in allms]
+    else:
+        per_rank = [ms_local]
+    ms = float(tmax[0])
+    peaks, peak_src = load_peaks()
+    res = {"value": T_total * P / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "scaling": "strong",
+           "frames_total": T_total, "frames_per_gpu": T, "points": P, "precision": args.precision,
+           "dims": dict(zip(("cin", "L", "cout", "nl", "H"), dims4)), "gather": mode, "per_rank_ms": per_rank,
+           "workload": "BASELINE.json configs[2]: case4 3-D shapes, 4096 frames x 131072 points, frame-sharded",
+           "roofline": roofline_block(dims4, T, P, float(tmax[1]), peaks, peak_src, args.precision, "tc_forward_kernel<384>")}
+    m4._timing = None
+    del fused, m4
+    torch.cuda.empty_cache()
+    return res
 
 
 def main_ours(args):
@@ -313,8 +491,7 @@ def main_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (no NCCL version banner)
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)  # NCCL's own logging is left to the environment (stderr)
 
     cin, L, cout, nl, H = DIMS
     T, P = args.frames, args.points
@@ -332,7 +509,8 @@ def main_ours(args):
             if args.gather == "nccl":
                 raise RuntimeError("NCCL all-gather requested")
             fused = cb.FusedGatherDecoder(model, T, P)
-            gather_mode = "fused into the decode kernel: epilogue stores to all ranks' symmetric-memory buffers over NVLink"
+            gather_mode = ("fused into the decode kernel: epilogue stores to all ranks' symmetric-memory buffers over "
+                           "NVLink (double-buffered)")
         except Exception as e:  # noqa: BLE001 - symmetric memory unavailable: decode + NCCL all_gather_into_tensor
             fused = None
             gathered = torch.empty((world * T, P, cout), dtype=torch.float32, device=dev)
@@ -379,6 +557,8 @@ def main_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms = float(t.item())
     value = world * T * P * args.steps / (step_ms * 1e-3)
+    del fused, gathered
+    torch.cuda.empty_cache()
 
     # ---- end to end through the reference-facing driver: host buffers in, host field out
     xn = Affine11(torch.tensor([1.0, 1.0]), torch.tensor([-1.0, -1.0]))
@@ -396,19 +576,39 @@ def main_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * T * P * e2e_steps / float(t.item())
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(coords_h.numel() * 4 + lat_h.numel() * 4),
+           "d2h_bytes_per_step": int(out_h.numel() * 4), "steps": e2e_steps,
+           "api": "confild_b200.decoder(coords, latents, model, x_normalizer, y_normalizer, 16, device) "
+                  "with pinned host buffers (mirror of cnf/inference_function.py:51-76)"}
+    # the wall the e2e number runs into: the same bytes device->host with NO decode, all ranks at once (max over ranks)
+    y_dev = torch.empty((T, P, cout), dtype=torch.float32, device=dev)
+    out_h.copy_(y_dev, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        out_h.copy_(y_dev, non_blocking=True)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    d2h_gbs = 3 * out_h.numel() * 4 / float(t.item()) / 1e9
+    e2e["d2h_only"] = {"gb_per_s_per_gpu": d2h_gbs, "gb_per_s_all_ranks": d2h_gbs * world,
+                       "point_frames_per_s_ceiling": world * T * P * 3 / float(t.item()),
+                       "note": "copy of the decoded field to pinned host memory alone, all ranks concurrently: the "
+                               "host-side ceiling of the e2e metric"}
+    del y_dev
 
     extra = {}
-    if world == 1 and not args.no_extra:
-        extra = measure_extra(model, coords, lat, dev, args)
+    if not args.no_extra:
+        if world == 1:
+            extra = measure_extra(model, coords, lat, dev, args)
+        del coords, lat, flush
+        torch.cuda.empty_cache()
+        extra["config3_case4_sharded"] = measure_config3(cb, dev, world, rank, args)
 
     if rank == 0:
         peaks, peak_src = load_peaks()
         kavg_ms = sum(kern_ms) / max(1, len(kern_ms))
-        fl = flops_per_pf(*DIMS) * T * P
-        ach_tf = fl / (kavg_ms * 1e-3) / 1e12
-        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-        sin_rate = sins_per_pf(*DIMS) * T * P / (kavg_ms * 1e-3)
-        mufu_peak = MUFU_PEAK_SIN_PER_S
         launch = _native.query_launch(model._cdims(), model._precision_code(), T, P)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -417,24 +617,14 @@ def main_ours(args):
             "config": {"workload": f"CNF decode {CASE} 2D shapes, {T} frames x {P} points per GPU, forward only "
                                    "(BASELINE.json configs[1])",
                        "dims": dict(zip(("cin", "L", "cout", "nl", "H"), DIMS)), "frames_per_gpu": T, "points": P,
-                       "precision": {"bf16x3": "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate",
-                                     "fp16": "tcgen05 single fp16 MMA per product, fp32 accumulate",
-                                     "fp32": "CUDA-core fp32 FMA"}[args.precision],
+                       "precision": cb.PRECISION_NOTES[args.precision],
                        "parallelism": f"frames sharded over {world} GPU(s)" + (f"; all-gather of the field inside the step, {gather_mode}" if world > 1 else ""),
                        "l2": "256 MiB memset between timed steps; each step also writes %.0f MB of output" % (T * P * cout * 4 / 1e6)},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(coords_h.numel() * 4 + lat_h.numel() * 4),
-                    "d2h_bytes_per_step": int(out_h.numel() * 4), "steps": e2e_steps,
-                    "api": "confild_b200.decoder(coords, latents, model, x_normalizer, y_normalizer, 16, device) "
-                           "with pinned host buffers (mirror of cnf/inference_function.py:51-76)"},
+            "e2e": e2e,
             "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                         "kernel": "tc2_forward_kernel" if args.precision != "fp32" else "simt_forward_kernel",
-                         "kernel_ms": kavg_ms, "peak_source": f"{peak_src} bf16_tflops_sustained",
-                         "algorithmic_flops_per_launch": fl,
-                         "mufu": {"achieved_gsin_s": sin_rate / 1e9, "measured_peak_gsin_s": mufu_peak / 1e9,
-                                  "frac": sin_rate / mufu_peak}},
+            "roofline": roofline_block(DIMS, T, P, kavg_ms, peaks, peak_src, args.precision,
+                                       "tc2_forward_kernel" if args.precision != "fp32" else "simt_forward_kernel"),
             "launch": dict(zip(("sms", "ctas", "threads", "smem_bytes", "ctas_per_sm", "tmem_cols", "tile_points"), launch)),
         }
         if cpu_base is not None:
@@ -457,8 +647,10 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("CONFILD_PRECISION", "bf16x3"), choices=["bf16x3", "fp16", "fp32"])
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--points", type=int, default=POINTS)
+    ap.add_argument("--config3-frames", type=int, default=CONFIG3_FRAMES, help="total frames of extra.config3_case4_sharded")
+    ap.add_argument("--config3-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the fast-mode and DPS side measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (other precisions, DPS, case4, config 3)")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N>1: how the decoded field is all-gathered")
     args = ap.parse_args()
     if args.impl == "reference":

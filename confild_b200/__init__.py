@@ -8,15 +8,16 @@ interface (``nf_networks``, ``inference_function``), frame sharding (``distribut
 sources + C ABI (``csrc/``, ``include/confild_cnf.h``).
 """
 from .nf_networks import (BatchLinear, Sine, SIRENAutodecoder_film, SIRENAutodecoder_film_extra_in,  # noqa: F401
-                          canonicalize, first_layer_sine_init, sine_init)
+                          canonicalize, first_layer_sine_init, sine_init, PRECISION_NOTES)
 from .inference_function import decoder, pass_through_model_batch  # noqa: F401
 from .folding import fold_normalizers  # noqa: F401
+from .dps import measurement_norm, sensor_rows  # noqa: F401
 from .distributed import FusedGatherDecoder, all_gather_frames, decode_frame_sharded, shard_bounds  # noqa: F401
 
 __all__ = [
     "SIRENAutodecoder_film", "SIRENAutodecoder_film_extra_in", "BatchLinear", "Sine",
     "decoder", "pass_through_model_batch", "decode_frame_sharded", "all_gather_frames", "shard_bounds",
-    "FusedGatherDecoder", "fold_normalizers",
+    "FusedGatherDecoder", "fold_normalizers", "measurement_norm", "sensor_rows",
     "install",
 ]
 

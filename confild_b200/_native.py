@@ -20,13 +20,23 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
 EXPORTS = [
     "cnf_abi_version", "cnf_last_error", "cnf_tc_supported", "cnf_param_count", "cnf_packed_bytes",
     "cnf_pack_weights", "cnf_film_shift", "cnf_stash_bytes", "cnf_forward", "cnf_forward_gather", "cnf_backward",
-    "cnf_film_shift_backward", "cnf_query_launch",
+    "cnf_film_shift_backward", "cnf_film_shift_backward_scaled", "cnf_forward_loss", "cnf_query_launch",
+    "cnf_set_debug_knob",
 ]
+ABI_VERSION = 2
+LOSS_PARTIALS = 4096  # CNF_LOSS_PARTIALS
 
 
 class CnfDims(ctypes.Structure):
     _fields_ = [("cin", ctypes.c_int32), ("L", ctypes.c_int32), ("H", ctypes.c_int32),
                 ("nl", ctypes.c_int32), ("cout", ctypes.c_int32)]
+
+
+class CnfSensorLoss(ctypes.Structure):
+    """``cnf_sensor_loss`` of include/confild_cnf.h."""
+    _fields_ = [("d_y_meas", ctypes.c_void_p), ("d_mask", ctypes.c_void_p), ("mask_kind", ctypes.c_int32),
+                ("y_scale", ctypes.c_float * 4), ("y_offset", ctypes.c_float * 4),
+                ("d_gy", ctypes.c_void_p), ("d_partials", ctypes.c_void_p), ("d_norm", ctypes.c_void_p)]
 
 
 _lib: Optional[ctypes.CDLL] = None
@@ -42,10 +52,16 @@ def load() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path) and "CONFILD_CNF_LIB" not in os.environ:
-        try:  # the library is a build artefact (git-ignored): compile it on first use when nvcc is around
+    if "CONFILD_CNF_LIB" not in os.environ and _build.is_stale():
+        # the library is a build artefact (git-ignored): (re)compile it when it is missing or older than its sources
+        # and nvcc is around.  build() serialises concurrent ranks on a file lock and replaces the file atomically.
+        try:
             _build.build()
         except Exception as e:  # noqa: BLE001
+            if os.path.exists(path):
+                raise RuntimeError(
+                    f"{path} is older than its sources and rebuilding it failed ({e}); rebuild with "
+                    "`python -m confild_b200.build --force`") from e
             raise RuntimeError(
                 f"{path} not found and building it failed ({e}); build it with `python -m confild_b200.build` "
                 "(there is no CPU or PyTorch fallback for the CNF decode path)") from e
@@ -80,10 +96,17 @@ def load() -> ctypes.CDLL:
     lib.cnf_backward.argtypes = [dp, vp, i32, vp, vp, sz, vp, i64, i64, vp]
     lib.cnf_film_shift_backward.restype = i32
     lib.cnf_film_shift_backward.argtypes = [dp, vp, vp, i64, vp, vp]
+    lib.cnf_film_shift_backward_scaled.restype = i32
+    lib.cnf_film_shift_backward_scaled.argtypes = [dp, vp, vp, i64, vp, vp, vp]
+    lib.cnf_set_debug_knob.restype = i32
+    lib.cnf_set_debug_knob.argtypes = [ctypes.c_char_p, i32]
+    lib.cnf_forward_loss.restype = i32
+    lib.cnf_forward_loss.argtypes = [dp, vp, i32, vp, i64, vp, vp, i64, i64, vp, sz, ctypes.POINTER(CnfSensorLoss), vp]
     lib.cnf_query_launch.restype = i32
     lib.cnf_query_launch.argtypes = [dp, i32, i64, i64, ctypes.POINTER(i64), i32]
-    if lib.cnf_abi_version() != 1:
-        raise RuntimeError(f"{path}: ABI version {lib.cnf_abi_version()} != 1")
+    if lib.cnf_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{path}: ABI version {lib.cnf_abi_version()} != {ABI_VERSION}; rebuild with "
+                           "`python -m confild_b200.build --force`")
     _lib = lib
     return lib
 
@@ -92,6 +115,14 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().cnf_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+#: defaults of the debug knobs (cnf_set_debug_knob); the environment variables of the same names set the initial values
+KNOB_DEFAULTS = {"CNF_TC2": 1, "CNF_TC_STAGES": 0, "CNF_TC_PACKED": -1}
+
+
+def set_knob(name: str, value: int) -> None:
+    check(load().cnf_set_debug_knob(name.encode(), int(value)), "cnf_set_debug_knob")
 
 
 def dims(cin: int, L: int, H: int, nl: int, cout: int) -> CnfDims:

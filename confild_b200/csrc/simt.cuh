@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "layout.cuh"
+#include "tc_common.cuh"
 
 namespace cnf {
 
@@ -68,9 +69,10 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict_
 // The DPS shapes have few frames (T = 64..384) and a long reduction (K = 1408..6144): a (frame, K-chunk) grid with
 // split-K atomics keeps every SM busy where a 64x64-tile GEMM would run on one or two blocks.  glat is pre-zeroed.
 constexpr int kShiftBwdChunk = 128;
+// `scale` (optional, device): every output is multiplied by *scale -- the 1/||r|| of the fused DPS loss.
 __global__ void __launch_bounds__(128) film_shift_backward_kernel(const float* __restrict__ gshift,
                                                                   const float* __restrict__ V, float* __restrict__ glat,
-                                                                  int K, int L) {
+                                                                  int K, int L, const float* __restrict__ scale) {
   __shared__ float gs[kShiftBwdChunk];
   const int64_t t = blockIdx.x;
   const int i0 = blockIdx.y * kShiftBwdChunk;
@@ -81,7 +83,54 @@ __global__ void __launch_bounds__(128) film_shift_backward_kernel(const float* _
     float acc = 0.f;
 #pragma unroll 8
     for (int i = 0; i < n; ++i) acc = fmaf(gs[i], __ldg(V + (size_t)(i0 + i) * L + j), acc);
-    atomicAdd(glat + t * L + j, acc);
+    atomicAdd(glat + t * L + j, scale ? acc * __ldg(scale) : acc);
+  }
+}
+
+// Fused-loss finalize: ||r|| = sqrt(sum of the head warps' partial sums of r^2), summed in double in a fixed order.
+// norm[0] = ||r||, norm[1] = 1/||r|| (0 when ||r|| == 0: the subgradient torch.linalg.norm's backward uses).
+__global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __restrict__ partials, int n,
+                                                             float* __restrict__ norm) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partials[i];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (threadIdx.x == 0) {
+      const double nrm = sqrt(v);
+      norm[0] = (float)nrm;
+      norm[1] = nrm > 0.0 ? (float)(1.0 / nrm) : 0.f;
+    }
+  }
+}
+
+// Fused-loss epilogue of the fp32 (CUDA-core) path as its own pass over the decoded field: residual, seed and partial
+// sums exactly as the tensor-core kernels' heads do (tc_common.cuh: tc_loss_row).  One partial slot per block.
+__global__ void __launch_bounds__(256) loss_rows_kernel(LossArgs la, const float* __restrict__ y, int64_t T, int64_t P,
+                                                        int cout) {
+  __shared__ float red[8];
+  float sq = 0.f;
+  const int64_t rows = T * P;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < rows; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = q / P, p = q - t * P;
+    float ys[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int o = 0; o < cout; ++o) ys[o] = y[q * cout + o];
+    sq += tc_loss_row(la, t, p, P, cout, true, ys);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w];
+    la.partials[blockIdx.x % kLossPartials] = v;
   }
 }
 

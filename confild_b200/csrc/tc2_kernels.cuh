@@ -111,7 +111,7 @@ __device__ __forceinline__ constexpr int tc2_group_col(int hf, int c) { return 3
 struct Tc2NoHook {
   __device__ __forceinline__ void operator()() const {}
 };
-template <int PREC, bool REDUCE, bool LAST, bool STASH, typename HalfHook = Tc2NoHook>
+template <int PREC, bool LAST, bool STASH, typename HalfHook = Tc2NoHook>
 __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tmem_a, int hf,
                                                  const float* __restrict__ sbuf, const float* __restrict__ w_out_s,
                                                  int cout, float (&y)[4], __half* stash_l, uint64_t* a_half,
@@ -121,7 +121,7 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
   ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, 0), v[0]);
   ptx::tmem_wait_ld();
   ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, 1), v[1]);
-  tc_sines16<REDUCE, STASH>(v[0], sbuf + tc2_group_col(hf, 0), hnext,
+  tc_sines16<STASH>(v[0], sbuf + tc2_group_col(hf, 0), hnext,
                              STASH ? stash_l + (size_t)tc2_group_col(hf, 0) * kTileM : nullptr);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -131,7 +131,7 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
     if (c + 1 < 4) {
       const int c1 = tc2_group_col(hf, c + 1);
       ptx::tmem_wait_ld();
-      tc_sines16<REDUCE, STASH>(v[(c + 1) & 1], sbuf + c1, hnext, STASH ? stash_l + (size_t)c1 * kTileM : nullptr);
+      tc_sines16<STASH>(v[(c + 1) & 1], sbuf + c1, hnext, STASH ? stash_l + (size_t)c1 * kTileM : nullptr);
       if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, c + 2), v[c & 1]);
     }
     if (!LAST) {
@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
                                                                      int64_t coord_frame_stride,
                                                                      const float* __restrict__ shift,
                                                                      OutTargets outs, __half* __restrict__ stash,
-                                                                     int64_t T, int64_t P, int num_stages) {
-  constexpr bool REDUCE = false;  // hidden-layer arguments stay within ~10 rad: sin.approx is used directly
+                                                                     LossArgs loss, int64_t T, int64_t P,
+                                                                     int num_stages) {
   constexpr int pack_rows = PACKED ? 1 : 0;
   constexpr int H = kTc2H;
   constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
     const uint32_t bar_wg = 1 + g * 2 + hf;  // named barrier of this warpgroup (128 threads)
     const uint32_t bar_slot = 5 + g;         // named barrier of the slot's two warpgroups (256 threads)
     uint32_t d_phase = 0;
+    float loss_acc = 0.f;  // fused loss: this thread's share of sum r^2 over all its tiles (head warps only)
     CNF_TRACE_DECL;
     const bool tracer = (lane == 0);
     [[maybe_unused]] const int trole = 4 + warp;
@@ -330,11 +331,11 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         cur_layer = l;
         // two call sites so that each sees a pointer of known address space (ld.shared vs ld.global, not generic)
         if (!PACKED)
-          tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][l & 1], tail->w_out_s, cout,
+          tc2_hidden_layer<PREC, false, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][l & 1], tail->w_out_s, cout,
                                                        y, STASH ? st_row + (size_t)l * H * kTileM : nullptr,
                                                        &tail->a_half[g], &tail->a_full[g], half_hook);
         else
-          tc2_hidden_layer<PREC, REDUCE, false, STASH>(lane_base, tmem_a, hf, sh + (size_t)l * H, tail->w_out_s, cout, y,
+          tc2_hidden_layer<PREC, false, STASH>(lane_base, tmem_a, hf, sh + (size_t)l * H, tail->w_out_s, cout, y,
                                                        STASH ? st_row + (size_t)l * H * kTileM : nullptr,
                                                        &tail->a_half[g], &tail->a_full[g], half_hook);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
@@ -342,11 +343,11 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
       {
         layer_prologue(nl);
         if (!PACKED)
-          tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][nl & 1], tail->w_out_s, cout,
+          tc2_hidden_layer<PREC, true, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][nl & 1], tail->w_out_s, cout,
                                                       y, STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr,
                                                       nullptr);
         else
-          tc2_hidden_layer<PREC, REDUCE, true, STASH>(lane_base, tmem_a, hf, sh + (size_t)nl * H, tail->w_out_s, cout, y,
+          tc2_hidden_layer<PREC, true, STASH>(lane_base, tmem_a, hf, sh + (size_t)nl * H, tail->w_out_s, cout, y,
                                                       STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr, nullptr);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + nl);
       }
@@ -360,8 +361,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
 #pragma unroll
         for (int o = 0; o < 4; ++o)
           if (o < cout) ys[o] += __ldg(b_out + o);
+        if (loss.y_meas != nullptr) loss_acc += tc_loss_row(loss, t, p, P, cout, valid, ys);
         if (outs.n == 1) {  // local target: 4*cout bytes per row straight from registers (L2 merges the sectors)
-          if (valid) {
+          if (valid && outs.ptr[0] != nullptr) {  // (the fused-loss entry point may skip the decoded field)
             float* op = outs.ptr[0] + (t * P + p) * cout;
 #pragma unroll
             for (int o = 0; o < 4; ++o)
@@ -383,6 +385,11 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         tc_store_tile(outs, tail->y_stage[g], q0, nvalid, cout, hf * 128 + row, 256);
       }
       __syncwarp();  // the store loops have lane-dependent trip counts: reconverge before warp-aligned instructions
+    }
+    if (loss.y_meas != nullptr && hf == 0) {  // one slot per head warp: no atomics, deterministic
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+      if (lane == 0) loss.partials[(blockIdx.x * 8 + g * 4 + wq) % kLossPartials] = loss_acc;
     }
     ptx::tc_fence_before();
   } else if (warp < kMmaWarp + 2) {

@@ -17,11 +17,50 @@ constexpr int kMaxOutTargets = 8;
 struct OutTargets {
   float* ptr[kMaxOutTargets];
   int n;
+  int vec_ok;  // every target has the same 16-byte phase (checked on the host): the tile store may use 16-byte vectors
 };
+
+// Fused DPS measurement loss (reference: guided_diffusion/condition_methods.py:30-31 with the mask multiply of
+// measurements.py:91-97), evaluated in the forward kernel's head when y_meas != nullptr:
+//     y_phys = ya*y + yb                        (y_normalizer.denormalize folded into an affine map)
+//     r      = y_meas - mask * y_phys           (the residual whose Frobenius norm is the DPS distance; the operator
+//                                                returns mask*phy_fields, measurements.py:97 -- callers that want
+//                                                mask*(y_meas - y_phys) pass an already masked measurement)
+//     gy     = -ya * mask * r                   (= ||r|| * d||r||/dy: the backward seed, normalised later by 1/||r||)
+// Each head warp adds its sum of r^2 into its own slot of `partials` (no atomics, deterministic); a finalize kernel
+// reduces the slots to ||r|| and 1/||r||.
+constexpr int kLossPartials = 4096;  // slots: (CTA, head warp) -> CTA*8 + warp slot; covers 512 CTAs
+struct LossArgs {
+  const float* y_meas;  // (T, P, cout), nullptr = loss disabled
+  const float* mask;    // nullptr = all ones; else per kind below
+  int mask_kind;        // 1: (P) per point; 2: (P, cout); 3: (T, P, cout)
+  float ya[4], yb[4];
+  float* gy;            // (T, P, cout) out
+  float* partials;      // [kLossPartials] out, pre-zeroed
+};
+// Residual, seed and squared error of one decoded point (this thread's row): ys = network output (cout values).
+__device__ __forceinline__ float tc_loss_row(const LossArgs& la, int64_t t, int64_t p, int64_t P, int cout, bool valid,
+                                             const float (&ys)[4]) {
+  float sq = 0.f;
+  if (valid) {
+    const int64_t e = (t * P + p) * cout;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      if (o >= cout) continue;
+      float m = 1.f;
+      if (la.mask != nullptr)
+        m = la.mask_kind == 1 ? __ldg(la.mask + p) : la.mask_kind == 2 ? __ldg(la.mask + p * cout + o) : __ldg(la.mask + e + o);
+      const float r = __ldg(la.y_meas + e + o) - m * fmaf(la.ya[o], ys[o], la.yb[o]);
+      la.gy[e + o] = -la.ya[o] * m * r;
+      sq = fmaf(r, r, sq);
+    }
+  }
+  return sq;
+}
 
 #ifdef CNF_TRACE
 // Debug build only: per-role event trace of CTA 0 (role r writes (code, clock64) pairs at trace[r*8192 + 2*n]).
-__device__ unsigned long long* g_trace = nullptr;
+static __device__ unsigned long long* g_trace = nullptr;
 __device__ __forceinline__ void trace_event(unsigned long long* buf, int role, int& n, unsigned long long code) {
   if (buf != nullptr && n < 4000) {  // two fire-and-forget stores: the pointer was fetched once, at kernel start
     buf[role * 8192 + 2 * n] = code;
@@ -55,9 +94,14 @@ __device__ __forceinline__ void tc_stash16(__half* dst, const float (&c)[16]) {
   *reinterpret_cast<uint4*>(dst + kStashChunkStride) = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-template <bool REDUCE, bool STASH>
+// Hidden layers feed the pre-activation straight to sin.approx / cos.approx: MUFU's own range reduction (an fp32
+// multiply by 1/2pi, then the fractional turn) costs |z| * 2^-23 of absolute error, the same order as the fp32 rounding
+// of z itself in the reference, whatever |z| (tests: test_large_film_shifts_keep_parity); only layer 0 is reduced
+// explicitly.  SCALED: the accumulator holds S * (W h) (f16f8 precision, weights pre-scaled by a power of two per
+// layer) and `inv` = 1/S is folded into the FiLM add as one fma.
+template <bool STASH, bool SCALED = false>
 __device__ __forceinline__ void tc_sines16(const uint32_t (&v)[16], const float* __restrict__ sbuf, float (&h)[16],
-                                            __half* stash_dst) {
+                                            __half* stash_dst, float inv = 1.f) {
   float cs[16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -67,18 +111,21 @@ __device__ __forceinline__ void tc_sines16(const uint32_t (&v)[16], const float*
     // stash variant keeps scalar adds (its register pressure turns the 64-bit pairs into spills: measured 6% slower)
     float zs[4];
     if (!STASH) {
-      const float2 z01 = __fadd2_rn(make_float2(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1])),
-                                    make_float2(sv[0], sv[1]));
-      const float2 z23 = __fadd2_rn(make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3])),
-                                    make_float2(sv[2], sv[3]));
+      const float2 a01 = make_float2(__uint_as_float(v[q * 4 + 0]), __uint_as_float(v[q * 4 + 1]));
+      const float2 a23 = make_float2(__uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+      const float2 z01 = SCALED ? __ffma2_rn(a01, make_float2(inv, inv), make_float2(sv[0], sv[1]))
+                                : __fadd2_rn(a01, make_float2(sv[0], sv[1]));
+      const float2 z23 = SCALED ? __ffma2_rn(a23, make_float2(inv, inv), make_float2(sv[2], sv[3]))
+                                : __fadd2_rn(a23, make_float2(sv[2], sv[3]));
       zs[0] = z01.x; zs[1] = z01.y; zs[2] = z23.x; zs[3] = z23.y;
     } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) zs[e] = __uint_as_float(v[q * 4 + e]) + sv[e];
+      for (int e = 0; e < 4; ++e)
+        zs[e] = SCALED ? fmaf(__uint_as_float(v[q * 4 + e]), inv, sv[e]) : __uint_as_float(v[q * 4 + e]) + sv[e];
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float r = REDUCE ? ptx::reduce_2pi(zs[e]) : zs[e];
+      const float r = zs[e];
       h[q * 4 + e] = ptx::sin_approx_pinned(r);
       if (STASH) cs[q * 4 + e] = ptx::cos_approx(r);
     }
@@ -232,8 +279,8 @@ __device__ __forceinline__ void tc_store_tile(const OutTargets& outs, const floa
                                               int tid, int nthreads) {
   const int64_t e0 = q0 * cout;
   const int n = nvalid * cout;
-  // every target is the same offset into a (>= 256-byte aligned) buffer, so target 0 decides the alignment
-  if ((reinterpret_cast<uintptr_t>(outs.ptr[0] + e0) & 15) == 0) {
+  // vec_ok: all targets share target 0's 16-byte phase (host-checked), so target 0 decides the alignment
+  if (outs.vec_ok && (reinterpret_cast<uintptr_t>(outs.ptr[0] + e0) & 15) == 0) {
     const int n4 = n / 4;
     for (int i = tid; i < n4; i += nthreads) {
       const float4 v = *reinterpret_cast<const float4*>(ys + 4 * i);

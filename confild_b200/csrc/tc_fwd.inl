@@ -1,0 +1,51 @@
+// Launcher of tc_forward_kernel (H = 128 / 256 / 384) for ONE operand precision (CNF_TU_PREC); included by
+// tc_fwd_<precision>.cu so that every precision is its own translation unit.
+#include "tc_plan.cuh"
+
+namespace cnf {
+namespace host {
+namespace {
+
+template <int H, int PREC, bool STASH>
+int launch_tc_forward(const FwdArgs& a) {
+  static std::atomic<size_t> smem_set[2][kMaxDevices];
+  DeviceInfo di;
+  if (int rc = device_info(&di)) return rc;
+  const int pack_rows = use_packed(a.P);
+  const int64_t tiles = tc_num_tiles(a.T, a.P, pack_rows);
+  TcPlan plan;
+  if (int rc = make_tc_plan<H, PREC>(di, tiles, &plan)) return rc;
+  if (a.query) {
+    *a.query = LaunchInfo{plan.grid, kTcThreads, plan.smem, 1, (int)plan.tmem_cols, kTileM};
+    return CNF_OK;
+  }
+  // frame-aligned tiles of the block-pipelined kernels stage the layer's FiLM shifts in shared memory
+  constexpr bool kCanStage = TcCfg<H, PREC>::kBlockPipe;
+  const bool stage = kCanStage && !pack_rows;
+  auto kern = stage ? tc_forward_kernel<H, PREC, STASH, kCanStage> : tc_forward_kernel<H, PREC, STASH, false>;
+  if (int rc = ensure_smem(kern, plan.smem, di.device, smem_set[stage ? 1 : 0])) return rc;
+  kern<<<(unsigned)plan.grid, kTcThreads, plan.smem, a.stream>>>(a.d, a.packed, a.coords, a.coord_frame_stride, a.shift,
+                                                                a.outs, reinterpret_cast<__half*>(a.stash), a.loss, a.T,
+                                                                a.P, plan.stages, pack_rows);
+  CNF_CUDA(cudaGetLastError());
+  return CNF_OK;
+}
+
+template <int H>
+int dispatch_stash(const FwdArgs& a) {
+  return a.stash ? launch_tc_forward<H, CNF_TU_PREC, true>(a) : launch_tc_forward<H, CNF_TU_PREC, false>(a);
+}
+
+}  // namespace
+
+int CNF_TU_NAME(const FwdArgs& a) {
+  switch (a.d.H) {
+    case 128: return dispatch_stash<128>(a);
+    case 256: return dispatch_stash<256>(a);
+    case 384: return dispatch_stash<384>(a);
+  }
+  return fail(CNF_ERR_UNSUPPORTED, "no tensor-core kernel for H=%d", a.d.H);
+}
+
+}  // namespace host
+}  // namespace cnf

@@ -238,7 +238,7 @@ __device__ __forceinline__ void tc_wait_d_full(TcSmemTail* tail, int warp, uint3
 // 16-column groups.  Both groups are loaded at once; for n >= 1 the thread then arrives on d_drained[n] (the issuer may
 // overwrite the block with the next layer's Q'(n,0)); sines, bf16 split, store into K part n of the next A operand,
 // arrive on e_done[n].  LAST: output head instead of the stores, no arrivals.
-template <int H, int PREC, bool REDUCE, bool LAST, bool STASH>
+template <int H, int PREC, bool LAST, bool STASH>
 __device__ __forceinline__ void tc_block_epilogue(int n, uint8_t* a_smem, uint32_t tmem_row, int row, int cg,
                                                   const float* __restrict__ shl, const float* __restrict__ w_out,
                                                   int cout, float (&y)[4], __half* stash_l, TcSmemTail* tail) {
@@ -253,8 +253,8 @@ __device__ __forceinline__ void tc_block_epilogue(int n, uint8_t* a_smem, uint32
     ptx::tc_fence_before();
     ptx::mbar_arrive(&tail->d_drained[n]);
   }
-  tc_sines16<REDUCE, STASH>(v0, shl + c0, h0, STASH ? stash_l + (size_t)c0 * kTileM : nullptr);
-  tc_sines16<REDUCE, STASH>(v1, shl + c0 + 16, h1, STASH ? stash_l + (size_t)(c0 + 16) * kTileM : nullptr);
+  tc_sines16<STASH>(v0, shl + c0, h0, STASH ? stash_l + (size_t)c0 * kTileM : nullptr);
+  tc_sines16<STASH>(v1, shl + c0 + 16, h1, STASH ? stash_l + (size_t)(c0 + 16) * kTileM : nullptr);
   if (!LAST) {
     tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h0);
     tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0 + 16, h1);
@@ -356,13 +356,14 @@ __device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t 
 // ------------------------------------------------------------------ forward
 // STAGE (block pipeline, frame-aligned tiles only): the layer's FiLM shifts are staged in shared memory once per layer
 // instead of being read by every thread with warp-uniform global loads (the H=128 kernel lost 13-20 % without staging).
-template <int H, int PREC, bool STASH, bool REDUCE, bool STAGE = false>
+template <int H, int PREC, bool STASH, bool STAGE = false>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
                                                                    const float* __restrict__ coords,
                                                                    int64_t coord_frame_stride,
                                                                    const float* __restrict__ shift,
                                                                    OutTargets outs, __half* __restrict__ stash,
-                                                                   int64_t T, int64_t P, int num_stages, int pack_rows) {
+                                                                   LossArgs loss, int64_t T, int64_t P, int num_stages,
+                                                                   int pack_rows) {
   using C = TcCfg<H, PREC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -395,6 +396,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     [[maybe_unused]] float* shift_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tail) + kTcTailBytes +
                                                                (C::kABytes >= 4 * kTileM * 16 ? 0 : 4 * kTileM * 16));
     uint32_t d_phase = 0;
+    float loss_acc = 0.f;  // fused loss: this thread's share of sum r^2 (head warps: cg == 0)
     CNF_TRACE_DECL;
     const bool tracer = (lane == 0);
     [[maybe_unused]] const int trole = 4 + warp;
@@ -471,14 +473,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
             // two call sites per variant so that each sees a pointer of known address space (ld.shared vs ld.global)
             if constexpr (STAGE) {
               if (!last)
-                tc_block_epilogue<H, PREC, REDUCE, false, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail);
+                tc_block_epilogue<H, PREC, false, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail);
               else
-                tc_block_epilogue<H, PREC, REDUCE, true, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail);
+                tc_block_epilogue<H, PREC, true, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail);
             } else {
               if (!last)
-                tc_block_epilogue<H, PREC, REDUCE, false, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+                tc_block_epilogue<H, PREC, false, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
               else
-                tc_block_epilogue<H, PREC, REDUCE, true, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+                tc_block_epilogue<H, PREC, true, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
             }
             if (tracer) CNF_TRACE_EVENT(trole, 600 + 10 * l + n);  // epilogue of block n done
           }
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
             ptx::tmem_ld_32x32b_x16(tmem_row + c0, v);
             ptx::tmem_wait_ld();
             float h[16];
-            tc_sines16<REDUCE, STASH>(v, shl + c0, h, STASH ? st_row + ((size_t)l * H + c0) * kTileM : nullptr);
+            tc_sines16<STASH>(v, shl + c0, h, STASH ? st_row + ((size_t)l * H + c0) * kTileM : nullptr);
             if (!last) {
               tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
             } else {
@@ -538,8 +540,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
 #pragma unroll
         for (int o = 0; o < 4; ++o)
           if (o < cout) ys[o] += __ldg(b_out + o);
+        if (loss.y_meas != nullptr) loss_acc += tc_loss_row(loss, t, p, P, cout, valid, ys);
         if (outs.n == 1) {  // local target: straight from registers
-          if (valid) {
+          if (valid && outs.ptr[0] != nullptr) {
             float* op = outs.ptr[0] + (t * P + p) * cout;
 #pragma unroll
             for (int o = 0; o < 4; ++o)
@@ -560,6 +563,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
       }
       __syncwarp();
       ptx::bar_sync(1, kTcEpiWarps * 32);  // partial sums consumed before the next tile's layer 0 overwrites them
+    }
+    if (loss.y_meas != nullptr && cg == 0) {  // one slot per head warp: no atomics, deterministic
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+      if (lane == 0) loss.partials[(blockIdx.x * 8 + wq) % kLossPartials] = loss_acc;
     }
     ptx::tc_fence_before();
   } else if (warp < kTcEpiWarps + kTcIssuerWarps) {

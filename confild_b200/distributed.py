@@ -96,15 +96,24 @@ class FusedGatherDecoder:
     Every rank allocates the gathered field ``(world*T_local, P, cout)`` in torch symmetric memory and maps its peers'
     buffers; ``__call__`` then runs ``cnf_forward_gather``: the kernel's epilogue stores each decoded point straight
     into all ``world`` buffers (12 bytes per point and target over NVLink), so there is no separate collective pass --
-    only a barrier.  Equal shards only (``T_local`` frames per rank).  The returned tensor is the rank's symmetric
-    buffer: consume (or copy) it before the next call, which overwrites it on every rank.
+    only a device-side barrier after the stores.  Equal shards only (``T_local`` frames per rank).
+
+    Cross-rank ordering.  The trailing barrier of call k tells every rank that all stores of call k have landed.  It
+    does NOT stop a fast rank from starting call k+1 while a slow peer is still reading call k's result, so the
+    symmetric allocation is double-buffered (``buffers=2``): call k writes buffer ``k % 2``.  A rank can only reach
+    call k+2 (which overwrites buffer ``k % 2`` again) after passing the barrier of call k+1, i.e. after every peer has
+    ENQUEUED call k+1 -- and a peer's reads of call k's result precede its call k+1 in stream order.  Contract: consume
+    (or copy) the returned tensor on the calling stream before the next-but-one call.  ``buffers=1`` keeps a single
+    buffer and adds a leading barrier instead (half the memory, one more barrier per call).
     """
 
-    def __init__(self, model, T_local: int, P: int, group=None):
+    def __init__(self, model, T_local: int, P: int, group=None, buffers: int = 2):
         import torch.distributed._symmetric_memory as symm_mem
 
         if not dist.is_initialized():
             raise RuntimeError("FusedGatherDecoder needs an initialised process group")
+        if buffers not in (1, 2):
+            raise ValueError("buffers must be 1 or 2")
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
@@ -113,13 +122,22 @@ class FusedGatherDecoder:
         self.model, self.T_local, self.P = model, int(T_local), int(P)
         cout = int(model.net1[-1].weight.shape[0])
         dev = model.net1[0].weight.device
-        self.buf = symm_mem.empty((self.world * self.T_local, self.P, cout), dtype=torch.float32, device=dev)
+        self.buffers = buffers
+        # one symmetric allocation holding `buffers` gathered fields back to back (one rendezvous, one signal pad)
+        self.buf = symm_mem.empty((buffers, self.world * self.T_local, self.P, cout), dtype=torch.float32, device=dev)
         self.handle = symm_mem.rendezvous(self.buf, self.group)
         block_bytes = self.T_local * self.P * cout * 4
-        # every rank's buffer, offset to THIS rank's frame range
-        self.out_ptrs = [int(p) + self.rank * block_bytes for p in self.handle.buffer_ptrs]
+        field_bytes = self.world * block_bytes
+        # every rank's buffer b, offset to THIS rank's frame range
+        self.out_ptrs = [[int(p) + b * field_bytes + self.rank * block_bytes for p in self.handle.buffer_ptrs]
+                         for b in range(buffers)]
+        self.calls = 0
 
     def __call__(self, coords: torch.Tensor, latents_local: torch.Tensor) -> torch.Tensor:
-        self.model.decode_into(coords, latents_local, self.out_ptrs, T_expected=self.T_local)
+        b = self.calls % self.buffers
+        self.calls += 1
+        if self.buffers == 1:
+            self.handle.barrier()  # every peer has finished reading the previous result (stream-ordered)
+        self.model.decode_into(coords, latents_local, self.out_ptrs[b], T_expected=self.T_local)
         self.handle.barrier()  # all ranks' stores have landed (stream-ordered device barrier over the signal pads)
-        return self.buf
+        return self.buf[b]

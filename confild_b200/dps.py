@@ -1,0 +1,150 @@
+"""Fused DPS measurement distance and its latent gradient (second half).
+
+One guided-sampling step of the reference evaluates (guided_diffusion/condition_methods.py:28-33)
+
+    difference = measurement - operator.forward(x_0_hat)      # operator.forward = [mask *] denormalize(decode(...))
+    norm       = torch.linalg.norm(difference)
+    norm_grad  = torch.autograd.grad(norm, x_prev)[0]
+
+i.e. decode, four element-wise passes over ``(T, P, cout)`` and their autograd mirror images around the two CNF
+kernels.  ``measurement_norm`` computes the same ``norm`` with the residual, its squared sum and the backward seed
+produced inside the decode kernel's head (``cnf_forward_loss``), runs the chain backward right away and scales by
+``1/norm`` on the device (``cnf_film_shift_backward_scaled``): K1 -> forward+loss -> finalize -> backward -> K4, no
+PyTorch element-wise kernel and no host synchronisation.  The returned scalar is differentiable with respect to the
+latents (and through them to ``x_prev`` / the U-Net), so ``torch.autograd.grad(norm, x_prev)`` works unchanged.
+
+``sensor_rows`` is the helper for the dense-grid operators (Case2-style mask over the full grid): it gathers the
+coordinates / measurements of the rows the mask keeps, so that decode + backward run on the sensor rows only.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native
+from .folding import _affine_of_normalizer
+from .nf_networks import SIRENAutodecoder_film, canonicalize
+
+
+def _mask_kind(mask: torch.Tensor, T: int, P: int, cout: int) -> Tuple[torch.Tensor, int]:
+    """Canonical device layout of the mask: kind 1 (P), 2 (P,cout) or 3 (T,P,cout)."""
+    m = mask.to(torch.float32)
+    if m.numel() == P:  # per point: (P,), (P,1), (1,P,1) ...
+        return m.reshape(P).contiguous(), 1
+    if m.numel() == P * cout and m.shape[-1] == cout:
+        return m.reshape(P, cout).contiguous(), 2
+    return m.expand(torch.broadcast_shapes(tuple(m.shape), (T, P, cout))).reshape(T, P, cout).contiguous(), 3
+
+
+class _MeasurementNormFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, lat2d, coords_c, frame_stride, module, y_meas, mask, mask_kind, ya, yb, want_grad, want_field):
+        lib = _native.load()
+        d = module._cdims()
+        cin, L, H, nl, cout = module._dims_tuple
+        T, P = lat2d.shape[0], coords_c.shape[-2]
+        prec = module._precision_code()
+        dev = lat2d.device
+        packed = module._ensure_packed()
+        shift = torch.empty((T, (nl + 1) * H), dtype=torch.float32, device=dev)
+        field = torch.empty((T, P, cout), dtype=torch.float32, device=dev) if (
+            want_field or prec == _native.PREC_FP32) else None
+        gy = torch.empty((T, P, cout), dtype=torch.float32, device=dev)
+        partials = torch.empty(_native.LOSS_PARTIALS, dtype=torch.float32, device=dev)
+        norm = torch.empty(2, dtype=torch.float32, device=dev)
+        stash, stash_n = None, 0
+        if want_grad:
+            stash_n = _native.stash_bytes(d, prec, T, P)
+            stash = torch.empty(stash_n, dtype=torch.uint8, device=dev)
+        loss = _native.CnfSensorLoss()
+        loss.d_y_meas = y_meas.data_ptr()
+        loss.d_mask = mask.data_ptr() if mask is not None else None
+        loss.mask_kind = int(mask_kind)
+        for o in range(4):
+            loss.y_scale[o] = float(ya[o]) if o < cout else 1.0
+            loss.y_offset[o] = float(yb[o]) if o < cout else 0.0
+        loss.d_gy, loss.d_partials, loss.d_norm = gy.data_ptr(), partials.data_ptr(), norm.data_ptr()
+        glat = None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _native.check(lib.cnf_film_shift(d, packed.data_ptr(), lat2d.data_ptr(), T, shift.data_ptr(), stream),
+                          "cnf_film_shift")
+            _native.check(lib.cnf_forward_loss(d, packed.data_ptr(), prec, coords_c.data_ptr(), frame_stride,
+                                               shift.data_ptr(), field.data_ptr() if field is not None else None, T, P,
+                                               stash.data_ptr() if stash is not None else None, stash_n,
+                                               ctypes.byref(loss), stream), "cnf_forward_loss")
+            if want_grad:  # the gradient is a by-product of the step: run the chain backward now and free the stash
+                gshift = torch.empty((T, (nl + 1) * H), dtype=torch.float32, device=dev)
+                glat = torch.empty((T, L), dtype=torch.float32, device=dev)
+                _native.check(lib.cnf_backward(d, packed.data_ptr(), prec, gy.data_ptr(), stash.data_ptr(), stash_n,
+                                               gshift.data_ptr(), T, P, stream), "cnf_backward")
+                _native.check(lib.cnf_film_shift_backward_scaled(d, packed.data_ptr(), gshift.data_ptr(), T,
+                                                                 norm[1:].data_ptr(), glat.data_ptr(), stream),
+                              "cnf_film_shift_backward_scaled")
+        ctx.glat = glat
+        ctx.mark_non_differentiable(*( [field] if field is not None else []))
+        out_norm = norm[0]
+        if field is not None:
+            return out_norm, field
+        return out_norm, torch.empty(0, device=dev)
+
+    @staticmethod
+    def backward(ctx, gnorm, _gfield):
+        if ctx.glat is None:
+            raise RuntimeError("measurement_norm was evaluated without gradient tracking of the latents")
+        return ctx.glat * gnorm, None, None, None, None, None, None, None, None, None, None
+
+
+def measurement_norm(model: SIRENAutodecoder_film, coords: torch.Tensor, latents: torch.Tensor,
+                     measurement: torch.Tensor, mask: Optional[torch.Tensor] = None, y_normalizer=None,
+                     mask_measurement: bool = False, return_field: bool = False):
+    """``torch.linalg.norm(measurement - mask * y_normalizer.denormalize(model(coords, latents)))`` as one fused
+    CUDA pass, differentiable with respect to ``latents``.
+
+    ``coords`` / ``latents`` follow ``model.forward``'s broadcasting; ``measurement`` broadcasts to the decoded field
+    ``(..., cout)``; ``mask`` (optional) is per point ``(P,)`` / ``(P, 1)``, per point and channel ``(P, cout)`` or full.
+    ``mask_measurement=True`` evaluates ``mask * (measurement - y)`` instead by masking the
+    measurement first.  ``y_normalizer`` is the reference's ``Normalizer_ts`` (any of its affine methods) or ``None``.
+    With ``return_field=True`` returns ``(norm, y_phys)`` where ``y_phys`` is the decoded (denormalised, unmasked) field.
+    """
+    dev = model._check_inputs(coords, latents)
+    grad_on = model._check_grad_mode(coords)
+    cin, L, H, nl, cout = model._dims_tuple
+    coords_c, stride, lat2d, T, P, out_lead = canonicalize(coords, latents)
+    if T * P == 0:
+        raise ValueError("empty decode")
+    if y_normalizer is not None:
+        ya, yb = _affine_of_normalizer(y_normalizer, True, cout, dev, torch.float32)
+        ya, yb = ya.tolist(), yb.tolist()
+    else:
+        ya, yb = [1.0] * cout, [0.0] * cout
+    y_meas = measurement.to(device=dev, dtype=torch.float32)
+    mk, kind = (None, 0)
+    if mask is not None:
+        mk, kind = _mask_kind(mask.to(dev), T, P, cout)
+        if mask_measurement:
+            mfull = mk.reshape((1, P, 1) if kind == 1 else (1, P, cout) if kind == 2 else (T, P, cout))
+            y_meas = y_meas.expand(out_lead + (cout,)).reshape(T, P, cout) * mfull
+    y_meas = y_meas.expand(out_lead + (cout,)).reshape(T, P, cout).contiguous()
+    want_grad = grad_on and lat2d.requires_grad
+    norm, field = _MeasurementNormFunction.apply(lat2d, coords_c, stride, model, y_meas, mk, kind, ya, yb, want_grad,
+                                                 return_field)
+    if return_field:
+        ya_t = torch.tensor(ya, device=dev)
+        yb_t = torch.tensor(yb, device=dev)
+        return norm, (field * ya_t + yb_t).reshape(out_lead + (cout,))
+    return norm
+
+
+def sensor_rows(coords: torch.Tensor, mask: torch.Tensor, *fields: torch.Tensor):
+    """Gather the rows a per-point ``mask (P,)`` keeps: returns ``(coords[idx], idx, *[f[..., idx, :] for f in fields])``.
+
+    For the dense-grid operators (the mask multiplies the decoded full grid, measurements.py:91-97) every masked-out
+    row contributes ``measurement**2`` to the norm and nothing to the gradient, so the guided step only needs the
+    decoder on the kept rows: ``measurement_norm(model, coords_s, latents, meas_s)`` on the gathered rows gives the
+    same latent gradient direction at ``len(idx)/P`` of the cost.
+    """
+    idx = torch.nonzero(mask.reshape(-1) != 0, as_tuple=False).reshape(-1)
+    return (coords.reshape(-1, coords.shape[-1])[idx], idx) + tuple(f[..., idx, :] for f in fields)

@@ -91,12 +91,18 @@ def decoder(coords, latents, model, x_normalizer, y_normalizer, batch_size, devi
             return out
         copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
-        pending = []
+        copied = []  # one event per chunk, recorded on the copy stream after its device->host copy
         sid = 0
         # one upload of all latents (T*L*4 bytes, tiny next to the field): a per-chunk synchronous copy would make the
         # host wait for the previous chunk's kernel before it can enqueue the next one
         lat_dev = latents.reshape(-1, 1, latent_size).to(dev, non_blocking=True)
-        for n in _chunk_plan(t_size, m_size, cout, batch_size):
+        for i, n in enumerate(_chunk_plan(t_size, m_size, cout, batch_size)):
+            # bounded device memory: before enqueueing chunk i the HOST waits until chunk i-3 has reached host memory
+            # (its buffers then return to the allocator), so at most three decoded chunks (x2 with the
+            # un-denormalised network output, <= 128 MiB each) are alive instead of the whole field; with a copy
+            # ~3x faster than the decode the wait returns long before the GPU runs out of queued work
+            if i >= 3:
+                copied[i - 3].synchronize()
             lat = lat_dev[sid:sid + n]
             chunk = y_normalizer.denormalize(model(coords_n, lat))
             done = torch.cuda.Event()
@@ -105,9 +111,10 @@ def decoder(coords, latents, model, x_normalizer, y_normalizer, batch_size, devi
                 copy_stream.wait_event(done)
                 out[sid:sid + n].copy_(chunk, non_blocking=True)
                 chunk.record_stream(copy_stream)
-            pending.append(chunk)
-            if len(pending) > 2:  # bound the number of in-flight device chunks
-                pending.pop(0)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            copied.append(ev)
+            del chunk
             sid += n
         copy_stream.synchronize()
     return out

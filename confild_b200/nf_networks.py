@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import math
 import os
+import warnings
 from typing import Optional, Tuple
 
 import torch
@@ -24,6 +25,13 @@ from torch import nn
 from . import _native
 
 DEFAULT_W0 = 30.0  # reference: cnf/initialization.py:5
+
+#: what each ``precision`` string means (bench.py prints it next to every number)
+PRECISION_NOTES = {
+    "bf16x3": "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate",
+    "fp16": "tcgen05 single fp16 MMA per product, fp32 accumulate",
+    "fp32": "CUDA-core fp32 FMA",
+}
 
 
 class Sine(nn.Module):
@@ -175,13 +183,16 @@ class SIRENAutodecoder_film(nn.Module):
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
         self._timing = None
+        self._warned_no_weight_grad = False
 
     # ------------------------------------------------------------------ reference API
     def disable_gradient(self):
         for param in self.parameters():
             param.requires_grad = False
 
-    def forward(self, coords, latents):
+    def _check_inputs(self, coords, latents) -> torch.device:
+        """Type / shape / dtype / device checks shared by every entry point (forward, decode_into, the fused loss):
+        raw device pointers cross the C ABI, so nothing unchecked may reach it."""
         if not (isinstance(coords, torch.Tensor) and isinstance(latents, torch.Tensor)):
             raise TypeError("coords and latents must be tensors")
         cin, L, H, nl, cout = self._dims_tuple
@@ -198,13 +209,32 @@ class SIRENAutodecoder_film(nn.Module):
                 ".to('cuda'); there is no CPU fallback")
         if coords.device != dev or latents.device != dev:
             raise RuntimeError(f"coords ({coords.device}) / latents ({latents.device}) must be on {dev}")
+        return dev
+
+    def _check_grad_mode(self, coords) -> bool:
+        """Returns whether autograd is recording.  Only dL/dlatents exists on this path: coordinates that require
+        grad and training mode raise; parameters that merely keep ``requires_grad=True`` (the DPS operators only call
+        ``.eval()``, measurements.py:209) are tolerated with a one-time warning, since they receive no gradient."""
         grad_on = torch.is_grad_enabled()
         if grad_on and coords.requires_grad:
             raise NotImplementedError("gradient with respect to coords is not implemented on this path")
-        if grad_on and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "weight gradients are not implemented (decode path only): call .eval() or disable_gradient() "
-                "for decoding / DPS, and use the reference module for training")
+        if grad_on and any(p.requires_grad for p in self.parameters()):
+            if self.training:
+                raise NotImplementedError(
+                    "weight gradients are not implemented (decode path only): call .eval() or disable_gradient() "
+                    "for decoding / DPS, and use the reference module for training")
+            if not self._warned_no_weight_grad:
+                self._warned_no_weight_grad = True
+                warnings.warn(
+                    "confild_b200.SIRENAutodecoder_film: parameters have requires_grad=True but this decode path "
+                    "only propagates gradients to the latents; parameter .grad stays None (call disable_gradient() "
+                    "to silence this)", stacklevel=3)
+        return grad_on
+
+    def forward(self, coords, latents):
+        self._check_inputs(coords, latents)
+        cin, L, H, nl, cout = self._dims_tuple
+        grad_on = self._check_grad_mode(coords)
         coords_c, stride, lat2d, T, P, out_lead = canonicalize(coords, latents)
         if T * P == 0:
             return coords.new_zeros(out_lead + (cout,))
@@ -292,12 +322,17 @@ class SIRENAutodecoder_film(nn.Module):
         this rank's frame range; see ``distributed.FusedGatherDecoder``).  No autograd.  Returns ``(T, P)``."""
         import ctypes
 
+        self._check_inputs(coords, latents)
         lib = _native.load()
         d = self._cdims()
         cin, L, H, nl, cout = self._dims_tuple
         coords_c, stride, lat2d, T, P, _ = canonicalize(coords, latents)
         if T_expected is not None and T != T_expected:
             raise ValueError(f"expected {T_expected} frames, got {T}")
+        if not 1 <= len(out_ptrs) <= 8:
+            raise ValueError(f"1..8 output targets, got {len(out_ptrs)}")
+        if any(int(p) == 0 or int(p) % 4 for p in out_ptrs):
+            raise ValueError("output targets must be non-NULL, 4-byte aligned device addresses")
         prec = self._precision_code()
         dev = lat2d.device
         packed = self._ensure_packed()

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define CNF_ABI_VERSION 1
+#define CNF_ABI_VERSION 2
 
 /* error codes */
 #define CNF_OK 0
@@ -59,6 +59,13 @@ typedef struct cnf_dims {
 /* Library / ABI version and the text of the last error raised on this thread. */
 int cnf_abi_version(void);
 const char* cnf_last_error(void);
+
+/* Debug / tuning knobs that select another schedule of the same arithmetic.  Their initial values come from the
+ * environment variables of the same name, read once per process; this call overrides one at run time (tests).
+ *   "CNF_TC2"        0: route H = 128 through the generic kernels (default 1)
+ *   "CNF_TC_STAGES"  n: cap the depth of the shared-memory weight ring (default 0 = as deep as fits)
+ *   "CNF_TC_PACKED"  0/1: force frame-aligned / packed tiles (default -1 = by shape) */
+int cnf_set_debug_knob(const char* name, int value);
 
 /* 1 if the tensor-core (tcgen05) kernels exist for these dims, else 0 (CUDA-core fp32 only). */
 int cnf_tc_supported(const cnf_dims* dims);
@@ -126,6 +133,39 @@ int cnf_backward(const cnf_dims* dims, const void* d_packed, int precision, cons
  * d_glatents (T,L). */
 int cnf_film_shift_backward(const cnf_dims* dims, const void* d_packed, const float* d_gshift, int64_t T,
                             float* d_glatents, void* stream);
+
+/* Same, with every output multiplied by the DEVICE scalar *d_scale (NULL = 1): the 1/||r|| of the fused
+ * measurement loss below, so that no host round trip or elementwise pass separates the kernels of a DPS step. */
+int cnf_film_shift_backward_scaled(const cnf_dims* dims, const void* d_packed, const float* d_gshift, int64_t T,
+                                   const float* d_scale, float* d_glatents, void* stream);
+
+/* Fused DPS measurement distance.  Replaces, for one guided-sampling step, the elementwise PyTorch passes between
+ * decode and autograd in the reference:
+ *     difference = measurement - operator.forward(x0_hat)        guided_diffusion/condition_methods.py:30
+ *                  (operator.forward = y_normalizer.denormalize(decode) [* mask])   measurements.py:91-97,222-226
+ *     norm = torch.linalg.norm(difference)                        condition_methods.py:31
+ *     autograd.grad(norm, x_prev)  -> dnorm/dy = -difference/norm condition_methods.py:32
+ * With y_phys = y_scale*y + y_offset (the output normaliser as an affine map per channel) and
+ * r = y_meas - mask*y_phys (the operator returns mask*phy_fields; pass an already masked measurement to obtain
+ * mask*(y_meas - y_phys)), cnf_forward_loss decodes like cnf_forward and, in the same kernel's head, writes
+ *     d_gy[t,p,o]  = -y_scale[o]*mask*r[t,p,o]        (= ||r|| * dnorm/dy, the seed of cnf_backward)
+ *     d_norm[0]    = ||r||_2 over all (t,p,o),  d_norm[1] = 1/||r||_2 (0 if ||r|| == 0)
+ * so a DPS step is cnf_film_shift -> cnf_forward_loss -> cnf_backward(d_gy) -> cnf_film_shift_backward_scaled(d_norm+1).
+ * d_out may be NULL for the tensor-core precisions when the decoded field itself is not needed. */
+#define CNF_LOSS_PARTIALS 4096
+typedef struct cnf_sensor_loss {
+  const float* d_y_meas; /* (T,P,cout) measurement, physical units                                        */
+  const float* d_mask;   /* NULL = no mask; else weights of kind mask_kind                               */
+  int32_t mask_kind;     /* 1: (P) per point, shared by frames and channels; 2: (P,cout); 3: (T,P,cout)  */
+  float y_scale[4];      /* y_phys = y_scale[o]*y + y_offset[o]; identity = 1, 0                          */
+  float y_offset[4];
+  float* d_gy;           /* (T,P,cout) out                                                                */
+  float* d_partials;     /* CNF_LOSS_PARTIALS floats of scratch (per-warp partial sums of r^2)            */
+  float* d_norm;         /* 2 floats out                                                                  */
+} cnf_sensor_loss;
+int cnf_forward_loss(const cnf_dims* dims, const void* d_packed, int precision, const float* d_coords,
+                     int64_t coord_frame_stride, const float* d_shift, float* d_out, int64_t T, int64_t P,
+                     void* d_stash, size_t stash_bytes, const cnf_sensor_loss* loss, void* stream);
 
 /* Introspection for the bench / tests: fills up to `n` int64 values:
  *   [0] SM count of the current device, [1] CTAs launched by cnf_forward for (precision,T,P),

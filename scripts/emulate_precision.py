@@ -1,0 +1,58 @@
+"""CPU emulation of tensor-core operand rounding for the hidden-layer chain (fp32 accumulate emulated in fp64).
+
+Modes: fp16 (single pass), bf16x3, f16f8 = fp16 main product + fp8 corrections
+  a*w ~= a16*w16 + e5m2(a - a16)*e4m3(w) + e4m3(a)*e4m3(w - w16)      (weights pre-scaled by a power of two S per layer)
+Prints forward rel-L2 vs the fp32 oracle for the four recipe shapes.  Test infrastructure (uses oracle/).
+"""
+import math, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from oracle import cnf_oracle as O
+
+E4, E5 = torch.float8_e4m3fn, torch.float8_e5m2
+
+def q(x, dt):
+    return x.to(dt).to(torch.float64)
+
+def chain(sd, coords, lat, mode, w0=30.0, a_lo_fmt=E5, a_lo_scale=1.0):
+    cin, L, cout, nl, H = O.dims_of(sd)
+    x = coords.double()
+    lat = lat.double()
+    for i in range(nl + 1):
+        W = sd[f"net1.{i}.weight"].double() * w0
+        shift = (sd[f"net1.{i}.bias"].double() + lat @ sd[f"net2.{i}.weight"].double().T) * w0   # (T,1,H)
+        if i == 0 or mode == "exact":
+            z = x @ W.T + shift
+        elif mode == "fp16":
+            z = q(x.float(), torch.float16) @ q(W.float(), torch.float16).T + shift
+        elif mode == "bf16x3":
+            a = x.float(); ah = a.bfloat16().float(); al = (a - ah).bfloat16().double(); ah = ah.double()
+            w = W.float(); wh = w.bfloat16().float(); wl = (w - wh).bfloat16().double(); wh = wh.double()
+            z = ah @ wh.T + al @ wh.T + ah @ wl.T + shift
+        elif mode == "f16f8":
+            S = 2.0 ** math.floor(math.log2(224.0 / W.abs().max().item()))
+            a = x.float(); a16 = a.half().float(); alo = q((a - a16) * a_lo_scale, a_lo_fmt) / a_lo_scale; a8 = q(a, E4)
+            w = (W * S).float(); w16 = w.half().float(); wlo8 = q(w - w16, E4); whi8 = q(w, E4)
+            z = (a16.double() @ w16.double().T + alo @ whi8.T + a8 @ wlo8.T) / S + shift
+        elif mode == "f16f8_wonly":   # 1.5 MMA: only the weight-residual correction
+            S = 2.0 ** math.floor(math.log2(224.0 / W.abs().max().item()))
+            a = x.float(); a16 = a.half().float(); a8 = q(a, E4)
+            w = (W * S).float(); w16 = w.half().float(); wlo8 = q(w - w16, E4)
+            z = (a16.double() @ w16.double().T + a8 @ wlo8.T) / S + shift
+        x = torch.sin(z).float().double()   # activations are fp32 in the kernel
+    return (x @ sd[f"net1.{nl+1}.weight"].double().T + sd[f"net1.{nl+1}.bias"].double())
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    for case in ("case1", "case2", "case3", "case4"):
+        dims = O.CASE_SHAPES[case]
+        sd = O.init_params(*dims, seed=0)
+        for sigma in (0.1, 1.0):
+            coords, lat = O.synthetic_inputs(dims[0], dims[1], 4, 1024, sigma=sigma)
+            ref = chain(sd, coords[None], lat[:, None], "exact")
+            ref32 = O.forward(sd, coords[None], lat[:, None])
+            row = [f"{case} sigma={sigma}: fp32-vs-fp64 {O.rel_l2(ref32, ref):.2e}"]
+            for mode in ("fp16", "bf16x3", "f16f8", "f16f8_wonly"):
+                row.append(f"{mode} {O.rel_l2(chain(sd, coords[None], lat[:, None], mode), ref):.2e}")
+            row.append(f"f16f8(e4m3 a_lo x2^8) {O.rel_l2(chain(sd, coords[None], lat[:, None], 'f16f8', a_lo_fmt=E4, a_lo_scale=256.0), ref):.2e}")
+            print("  ".join(row), flush=True)

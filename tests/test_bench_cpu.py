@@ -1,4 +1,5 @@
-"""CPU: the reference arm of bench.py (the oracle port on the host cores) prints one well-formed JSON line."""
+"""CPU: the reference arm of bench.py (the reference's own decoder from oracle/_ref when it was built, else the oracle
+port, on the host cores) prints one well-formed JSON line."""
 import json
 import os
 import subprocess
@@ -17,7 +18,8 @@ def test_reference_arm_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "cnf_decode_point_frames_per_s"
     assert d["unit"] == "point-frames/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ConditionalNeuralField", "cnf", "nf_networks.pyc"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("CNF decode case1")
 
@@ -51,3 +53,28 @@ def test_measured_arm_generators_match_the_oracle():
     assert set(got) == set(want)
     for k in want:
         assert torch.equal(got[k], want[k]), k
+
+
+def test_compiled_reference_matches_the_port():
+    """oracle/_ref (the reference's own modules, byte-compiled by oracle/build_ref.py) and the restated oracle give
+    bit-identical weights and outputs; skipped where neither /root/reference nor an earlier build exists."""
+    import sys as _sys
+
+    import pytest
+    import torch
+
+    _sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+    from oracle import cnf_oracle as O
+
+    if not build_ref.build():
+        pytest.skip("oracle/_ref not available (no /root/reference here and never built)")
+    Ref = build_ref.load_reference_class()
+    assert Ref.__module__ == "ConditionalNeuralField.cnf.nf_networks"
+    torch.manual_seed(0)
+    m = Ref(2, 128, 3, 10, 128).eval()
+    sd = O.init_params(2, 128, 3, 10, 128, seed=0)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    c, l = O.synthetic_inputs(2, 128, 2, 61)
+    assert torch.equal(m(c[None], l[:, None]), O.forward(sd, c[None], l[:, None]))

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_NAMES, golden_inputs, load_golden, sha_state
+from helpers import EXTRA_IN_NAMES, GOLDEN_NAMES, extra_in_inputs, golden_inputs, load_golden, sha_state
 from oracle import cnf_oracle as O
 
 
@@ -46,6 +46,18 @@ def test_latent_gradient_matches_golden(name):
     mask, y_meas = torch.from_numpy(g["mask"]), torch.from_numpy(g["y_meas"])
     loss, _, grad = O.grad_latents(sd, c, l, lambda y: O.sensor_loss(y, y_meas, mask))
     assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert O.rel_l2(grad.reshape(g["dlatents"].shape), torch.from_numpy(g["dlatents"])) < 1e-4
+
+
+@pytest.mark.parametrize("name", EXTRA_IN_NAMES)
+def test_extra_in_matches_golden(name):
+    """a8: SIRENAutodecoder_film_extra_in = the same chain on [extra, coords] (nf_networks.py:503-508)."""
+    g = load_golden(name)
+    sd, _, lat, cat = extra_in_inputs(g)
+    assert sha_state(sd) == str(g["weights_sha256"])
+    y = O.forward(sd, cat, lat)
+    assert O.rel_l2(y, torch.from_numpy(g["y"])) < 2e-6
+    grad = O.grad_latents_from_gout(sd, cat, lat, torch.from_numpy(g["gout"]))
     assert O.rel_l2(grad.reshape(g["dlatents"].shape), torch.from_numpy(g["dlatents"])) < 1e-4
 
 
