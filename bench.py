@@ -100,12 +100,13 @@ def reference_decoder(dims):
     oracle/_ref was never built.  Same seed-0 constructor weights either way (bit-identical, tests/test_oracle.py)."""
     cin, L, cout, nl, H = dims
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    why = "oracle/_ref not built"
     try:
         import build_ref  # the one other place bench.py executes oracle/
 
         Ref = build_ref.load_reference_class()
-    except Exception:  # noqa: BLE001
-        Ref = None
+    except Exception as e:  # noqa: BLE001
+        Ref, why = None, f"oracle/_ref failed to load: {type(e).__name__}: {e}"[:120]
     if Ref is not None:
         torch.manual_seed(0)
         model = Ref(cin, L, cout, nl, H).eval()
@@ -123,7 +124,7 @@ def reference_decoder(dims):
         with torch.no_grad():
             return O.forward(sd, coords[None], lat[:, None])
 
-    return decode_port, "port", "oracle/cnf_oracle.py restatement (oracle/_ref not built)"
+    return decode_port, "port", f"oracle/cnf_oracle.py restatement ({why})"
 
 
 def synthetic_inputs(cin, L, T, P, sigma=0.1, coord_seed=1, latent_seed=2):
@@ -368,7 +369,7 @@ def measure_extra(model, coords, lat, dev, args):
     cin, L, cout, nl, H = DIMS
     T, P = args.frames, args.points
     out = {}
-    for prec in ("bf16x3", "fp16"):
+    for prec in ("bf16x3", "f16f8", "fp16"):
         if prec == args.precision:
             continue
         other = cb.SIRENAutodecoder_film(cin, L, cout, nl, H, precision=prec)
@@ -644,7 +645,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CONFILD_PRECISION", "bf16x3"), choices=["bf16x3", "fp16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("CONFILD_PRECISION", "bf16x3"), choices=["bf16x3", "fp16", "f16f8", "fp32"])
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--points", type=int, default=POINTS)
     ap.add_argument("--config3-frames", type=int, default=CONFIG3_FRAMES, help="total frames of extra.config3_case4_sharded")

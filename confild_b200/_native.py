@@ -14,7 +14,8 @@ from . import build as _build
 PREC_FP32 = 0
 PREC_BF16X3 = 1
 PREC_FP16 = 2
-PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
+PREC_F16F8 = 3
+PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16, "f16f8": PREC_F16F8}
 
 #: every symbol include/confild_cnf.h declares (checked by tests/test_cabi.py)
 EXPORTS = [

@@ -57,21 +57,28 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > lib_m for d in _deps() if os.path.exists(d))
 
 
+TRACE_LIB_PATH = os.path.join(PKG_DIR, "libconfild_cnf_trace.so")  # -DCNF_TRACE build for tests/tools/trace_*.py
+
+
 def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    lib_path = TRACE_LIB_PATH if trace else LIB_PATH
+    obj_dir = OBJ_DIR + ("_trace" if trace else "")
+    if trace:
+        force = True
     if not force and not is_stale():
-        return LIB_PATH
+        return lib_path
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     with open(LOCK_PATH, "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
         try:
             if not force and not is_stale():  # another process built it while we waited for the lock
-                return LIB_PATH
+                return lib_path
             flags = NVCC_FLAGS + (["-DCNF_TRACE"] if trace else [])
             srcs = _sources()
 
             def compile_one(src):
-                obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+                obj = os.path.join(obj_dir, src[:-3] + ".o")
                 cmd = [nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
                 proc = subprocess.run(cmd, capture_output=True, text=True)
                 return src, obj, " ".join(cmd), proc.returncode, proc.stdout + proc.stderr
@@ -92,7 +99,7 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
                     os.unlink(tmp)
                 else:
                     os.chmod(tmp, 0o755)
-                    os.replace(tmp, LIB_PATH)  # atomic: a concurrent dlopen sees the old or the new file, never a part
+                    os.replace(tmp, lib_path)  # atomic: a concurrent dlopen sees the old or the new file, never a part
             with open(os.path.join(PKG_DIR, "build.log"), "w") as f:
                 f.write(log)
             if failed:
@@ -101,7 +108,7 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
                 print(log)
         finally:
             fcntl.flock(lock, fcntl.LOCK_UN)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

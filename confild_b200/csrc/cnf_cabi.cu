@@ -98,7 +98,9 @@ int check_dims(const cnf_dims* d) {
 
 bool tc_ok(const cnf_dims& d) { return cnf::tc_shape_ok(d.H) && d.nl >= 1 && d.cin <= 4 && d.cout <= 4; }
 
-bool is_tc_precision(int precision) { return precision == CNF_PREC_BF16X3 || precision == CNF_PREC_FP16; }
+bool is_tc_precision(int precision) {
+  return precision == CNF_PREC_BF16X3 || precision == CNF_PREC_FP16 || precision == CNF_PREC_F16F8;
+}
 
 // H = 128 fast path (activations in TMEM, two tiles in flight, one CTA per SM).
 bool use_tc2(const cnf_dims& d) { return d.H == 128 && cnf::host::knobs().tc2 != 0; }
@@ -114,9 +116,18 @@ int64_t simt_grid(int64_t tiles, int sms) {
 }
 
 int tc_forward_dispatch(int precision, const FwdArgs& a) {
-  if (use_tc2(a.d))
-    return precision == CNF_PREC_BF16X3 ? cnf::host::tc2_forward_bf16x3(a) : cnf::host::tc2_forward_fp16(a);
-  return precision == CNF_PREC_BF16X3 ? cnf::host::tc_forward_bf16x3(a) : cnf::host::tc_forward_fp16(a);
+  if (use_tc2(a.d)) {
+    switch (precision) {
+      case CNF_PREC_BF16X3: return cnf::host::tc2_forward_bf16x3(a);
+      case CNF_PREC_F16F8: return cnf::host::tc2_forward_f16f8(a);
+      default: return cnf::host::tc2_forward_fp16(a);
+    }
+  }
+  switch (precision) {
+    case CNF_PREC_BF16X3: return cnf::host::tc_forward_bf16x3(a);
+    case CNF_PREC_F16F8: return cnf::host::tc_forward_f16f8(a);
+    default: return cnf::host::tc_forward_fp16(a);
+  }
 }
 
 template <bool STASH>
@@ -192,6 +203,8 @@ extern "C" int cnf_debug_set_trace(void* d_buf) {
   int rc = 0;
   rc |= cnf::host::set_trace_tc2_fwd_bf16x3(p);
   rc |= cnf::host::set_trace_tc2_fwd_fp16(p);
+  rc |= cnf::host::set_trace_tc2_fwd_f16f8(p);
+  rc |= cnf::host::set_trace_tc_fwd_f16f8(p);
   rc |= cnf::host::set_trace_tc2_bwd(p);
   rc |= cnf::host::set_trace_tc_fwd_bf16x3(p);
   rc |= cnf::host::set_trace_tc_fwd_fp16(p);
@@ -246,6 +259,10 @@ int cnf_pack_weights(const cnf_dims* dims, const float* d_params_flat, float w0,
       cnf::pack_tc_kernel<<<592, 256, 0, st>>>(*dims, d_params_flat, w0, packed, mode);
       CNF_CUDA(cudaGetLastError());
     }
+    cnf::pack_scale_kernel<<<dims->nl, 256, 0, st>>>(*dims, d_params_flat, w0, packed);
+    CNF_CUDA(cudaGetLastError());
+    cnf::pack_tc_f8_kernel<<<592, 256, 0, st>>>(*dims, d_params_flat, w0, packed);
+    CNF_CUDA(cudaGetLastError());
   }
   return CNF_OK;
 }

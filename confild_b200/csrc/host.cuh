@@ -91,9 +91,11 @@ struct BwdArgs {
 // One function per (kernel family, precision): each lives in its own translation unit.
 int tc2_forward_bf16x3(const FwdArgs& a);
 int tc2_forward_fp16(const FwdArgs& a);
+int tc2_forward_f16f8(const FwdArgs& a);
 int tc2_backward(const BwdArgs& a);
 int tc_forward_bf16x3(const FwdArgs& a);
 int tc_forward_fp16(const FwdArgs& a);
+int tc_forward_f16f8(const FwdArgs& a);
 int tc_backward(const BwdArgs& a);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device): `slot` is a static array
@@ -110,6 +112,8 @@ inline int ensure_smem(Kernel kern, size_t smem, int device, std::atomic<size_t>
 #ifdef CNF_TRACE
 int set_trace_tc2_fwd_bf16x3(unsigned long long* p);
 int set_trace_tc2_fwd_fp16(unsigned long long* p);
+int set_trace_tc2_fwd_f16f8(unsigned long long* p);
+int set_trace_tc_fwd_f16f8(unsigned long long* p);
 int set_trace_tc2_bwd(unsigned long long* p);
 int set_trace_tc_fwd_bf16x3(unsigned long long* p);
 int set_trace_tc_fwd_fp16(unsigned long long* p);

@@ -32,6 +32,10 @@ struct PackedLayout {
   size_t tc_fwd_x3;  // [nl][stages_per_layer(H,2)][16 KiB] bf16 hi/lo of w0*W_l, operand B[n_out][k_in]
   size_t tc_fwd_h;   // [nl][stages_per_layer(H,1)][16 KiB] fp16
   size_t tc_bwd_x3;  // [nl][stages_per_layer(H,2)][16 KiB] bf16 hi/lo, operand B[k_in][n_out]
+  // f16f8 precision: per (K slab, row block) an fp16 stage of S_l*w0*W_l and an fp8 stage whose 128-byte rows hold
+  // [e4m3(S w)[k 0..63] | e4m3(S w - fp16(S w))[k 0..63]] of that slab; S_l = a power of two per layer
+  size_t tc_fwd_f8;  // [nl][stages_per_layer(H,2)][16 KiB]
+  size_t tc_scale;   // [2*nl] fp32: 1/S_l for l < nl, then S_l
   size_t total;
 };
 
@@ -55,6 +59,8 @@ __host__ __device__ inline PackedLayout make_layout(const cnf_dims& d) {
     p.tc_fwd_x3 = take(nl * (size_t)stages_per_layer(d.H, 2) * kStageBytes);
     p.tc_fwd_h = take(nl * (size_t)stages_per_layer(d.H, 1) * kStageBytes);
     p.tc_bwd_x3 = take(nl * (size_t)stages_per_layer(d.H, 2) * kStageBytes);
+    p.tc_fwd_f8 = take(nl * (size_t)stages_per_layer(d.H, 2) * kStageBytes);
+    p.tc_scale = take(2 * nl * sizeof(float));
   }
   p.total = off;
   return p;
@@ -86,6 +92,11 @@ __host__ __device__ inline ParamOffsets make_param_offsets(const cnf_dims& d) {
 // for the activation operand (r = query point).
 __host__ __device__ inline uint32_t sw128_offset(uint32_t r, uint32_t k) {
   return r * 128u + ((((k >> 3) ^ (r & 7u)) << 4) | ((k & 7u) << 1));
+}
+
+// Same layout for 8-bit elements: byte b in [0,128) of row r.
+__host__ __device__ inline uint32_t sw128_byte_offset(uint32_t r, uint32_t b) {
+  return r * 128u + ((((b >> 4) ^ (r & 7u)) << 4) | (b & 15u));
 }
 
 }  // namespace cnf

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "layout.cuh"
 
@@ -81,6 +82,63 @@ __global__ void pack_tc_kernel(cnf_dims d, const float* __restrict__ params, flo
     }
     uint8_t* dst = base + (l * spl + s) * (size_t)kStageBytes + sw128_offset(r, kk);
     *reinterpret_cast<uint16_t*>(dst) = bits;
+  }
+}
+
+// f16f8 precision, step 1: per hidden layer the power-of-two scale S_l that brings max|w0*W_l| just under 224 (so that
+// S*w fits e4m3's +-448 with headroom and fp16's range trivially); block l handles layer l.
+__global__ void __launch_bounds__(256) pack_scale_kernel(cnf_dims d, const float* __restrict__ params, float w0,
+                                                         uint8_t* __restrict__ packed) {
+  __shared__ float red[8];
+  const PackedLayout lay = make_layout(d);
+  const ParamOffsets po = make_param_offsets(d);
+  const size_t H = d.H, l = blockIdx.x;
+  const float* w = params + po.hid0 + l * (H * H + H);
+  float m = 0.f;
+  for (size_t i = threadIdx.x; i < H * H; i += blockDim.x) m = fmaxf(m, fabsf(w0 * w[i]));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    float S = 1.f;
+    if (m > 0.f && isfinite(m)) {
+      int e;
+      frexpf(224.f / m, &e);  // 224/m = f * 2^e, f in [0.5, 1)  ->  2^(e-1) <= 224/m
+      e = e - 1;
+      e = e > 30 ? 30 : (e < -30 ? -30 : e);
+      S = ldexpf(1.f, e);
+    }
+    float* sc = reinterpret_cast<float*>(packed + lay.tc_scale);
+    sc[l] = 1.f / S;
+    sc[d.nl + l] = S;
+  }
+}
+
+// f16f8 precision, step 2: the stage images.  One thread per weight element.
+__global__ void pack_tc_f8_kernel(cnf_dims d, const float* __restrict__ params, float w0, uint8_t* __restrict__ packed) {
+  const PackedLayout lay = make_layout(d);
+  const ParamOffsets po = make_param_offsets(d);
+  const size_t H = d.H, nl = d.nl;
+  const size_t nblocks = H / kStageRows;
+  const size_t spl = stages_per_layer(d.H, 2);
+  const float* sc = reinterpret_cast<const float*>(packed + lay.tc_scale);
+  uint8_t* base = packed + lay.tc_fwd_f8;
+  const size_t total = nl * H * H;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t l = i / (H * H), rem = i % (H * H), n = rem / H, k = rem % H;
+    const float w = w0 * params[po.hid0 + l * (H * H + H) + rem] * sc[nl + l];  // exact: S is a power of two
+    const __half h = __float2half_rn(w);
+    const float lo = w - __half2float(h);
+    const size_t ks = k / kSlabK, nb = n / kStageRows;
+    const uint32_t r = (uint32_t)(n % kStageRows), kk = (uint32_t)(k % kSlabK);
+    // stage order (as for the bf16 hi/lo image): K slab -> part -> 128-row block
+    uint8_t* st16 = base + (l * spl + (ks * 2 + 0) * nblocks + nb) * (size_t)kStageBytes;
+    uint8_t* st8 = base + (l * spl + (ks * 2 + 1) * nblocks + nb) * (size_t)kStageBytes;
+    *reinterpret_cast<uint16_t*>(st16 + sw128_offset(r, kk)) = __half_as_ushort(h);
+    st8[sw128_byte_offset(r, kk)] = (uint8_t)__nv_cvt_float_to_fp8(w, __NV_SATFINITE, __NV_E4M3);
+    st8[sw128_byte_offset(r, 64 + kk)] = (uint8_t)__nv_cvt_float_to_fp8(lo, __NV_SATFINITE, __NV_E4M3);
   }
 }
 

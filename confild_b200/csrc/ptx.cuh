@@ -1,6 +1,7 @@
 // Thin inline-PTX wrappers for the sm_100a features the CNF kernels use:
 // mbarrier, 1-D bulk TMA copies (cp.async.bulk), tcgen05 (alloc / mma / commit / ld / fences).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -113,6 +114,27 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 with 8-bit operands (e4m3 / e5m2 selected per operand in the instruction descriptor): K = 32 per
+// instruction, i.e. twice the K of kind::f16 in the same tensor-pipe time.  A in tensor memory: row i = TMEM lane i,
+// four 8-bit K elements per 32-bit column (element k in byte k % 4).
+__device__ __forceinline__ void umma_f8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on `bar` when every tcgen05 op issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -145,6 +167,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
                : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -184,6 +211,12 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t fmt, uint32_t M, 
          | ((M >> 4) << 24);  // M / 16
 }
 
+// Instruction descriptor for kind::f8f6f4: fp32 accumulate, A and B K-major; operand formats 0 = e4m3, 1 = e5m2.
+__host__ __device__ constexpr uint32_t make_idesc_f8(uint32_t a_fmt, uint32_t b_fmt, uint32_t M, uint32_t N) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+constexpr uint32_t kF8E4M3 = 0u, kF8E5M2 = 1u;
+
 // ---------------------------------------------------------------- small math helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {  // low half <- lo
   uint32_t r;
@@ -202,6 +235,35 @@ __device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_
 // One fma.f32x2 for both columns (exact: x - h = fma(h, -1, x)) instead of two scalar subtractions.
 __device__ __forceinline__ float2 bf16x2_residual(uint32_t hi, float x0, float x1) {
   return __ffma2_rn(make_float2(bf16lo_to_f32(hi), bf16hi_to_f32(hi)), make_float2(-1.f, -1.f), make_float2(x0, x1));
+}
+
+// Four fp32 values -> four 8-bit floats in one word (x0 in byte 0).  cvt.*x2 puts its FIRST source in the upper byte.
+__device__ __forceinline__ uint32_t pack_e4m3x4(float x0, float x1, float x2, float x3) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .b16 lo, hi;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 lo, %2, %1;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 hi, %4, %3;\n\t"
+      "mov.b32 %0, {lo, hi};\n\t}"
+      : "=r"(r)
+      : "f"(x0), "f"(x1), "f"(x2), "f"(x3));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_e5m2x4(float x0, float x1, float x2, float x3) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .b16 lo, hi;\n\t"
+      "cvt.rn.satfinite.e5m2x2.f32 lo, %2, %1;\n\t"
+      "cvt.rn.satfinite.e5m2x2.f32 hi, %4, %3;\n\t"
+      "mov.b32 %0, {lo, hi};\n\t}"
+      : "=r"(r)
+      : "f"(x0), "f"(x1), "f"(x2), "f"(x3));
+  return r;
+}
+// Residuals x - fp16(x) of the two values packed in `hi` (cvt.rn.f16x2: x0 in the low half): one fma.f32x2.
+__device__ __forceinline__ float2 f16x2_residual(uint32_t hi, float x0, float x1) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  return __ffma2_rn(h, make_float2(-1.f, -1.f), make_float2(x0, x1));
 }
 
 // "Pinned" variants: volatile asm keeps the program order of MUFU and pack instructions relative to each other, so a

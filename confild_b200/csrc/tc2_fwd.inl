@@ -30,6 +30,8 @@ int launch_tc2_forward(const FwdArgs& a) {
 }  // namespace
 
 int CNF_TU_NAME(const FwdArgs& a) {
+  if (CNF_TU_PREC == CNF_PREC_F16F8 && a.d.nl > kTc2MaxLayers)
+    return fail(CNF_ERR_UNSUPPORTED, "f16f8 supports up to %d hidden layers (got %d)", kTc2MaxLayers, a.d.nl);
   const bool pk = use_packed(a.P) != 0;
   if (a.stash)
     return pk ? launch_tc2_forward<CNF_TU_PREC, true, true>(a) : launch_tc2_forward<CNF_TU_PREC, true, false>(a);

@@ -29,6 +29,7 @@ constexpr int kTc2Threads = (kTc2EpiWarps + 3) * 32;   // + two MMA issuer warps
 // pool only holds what was released -- removed the stash variant's spills (-2.5 %) but cost the power-capped decode 2 %.)
 constexpr int kTc2BwdThreads = kTc2Threads;
 constexpr int kTc2SlotCols = 256;
+constexpr int kTc2MaxLayers = 64;  // hidden layers the f16f8 scale table holds (host-checked)
 
 struct Tc2SmemTail {
   float shift_s[2][2][kTc2H];   // [slot][layer parity][column]
@@ -43,14 +44,46 @@ struct Tc2SmemTail {
   uint64_t d_full[2];
   uint64_t turn[2];  // issue token passed between the two MMA issuer warps
   uint32_t tmem_base;
+  float inv_scale[kTc2MaxLayers];  // f16f8: 1/S_l per hidden layer (the accumulator holds S_l * W h)
 };
 
 __host__ __device__ constexpr size_t tc2_smem_bytes(int num_stages) {
   return 1024 + (size_t)num_stages * kStageBytes + sizeof(Tc2SmemTail);
 }
 
+// f16f8 operand of 16 activations (columns c0..c0+15 of this thread's row, c0 % 16 == 0), TMEM columns relative to the
+// slot's A area (128 columns): fp16 copy in [0,64) as for the other precisions; the 8-bit operand of K slab s = c0/64 in
+// [64 + 32s, +32): bytes [0,64) = e5m2(a - fp16(a)) and bytes [64,128) = e4m3(a) of the slab's 64 columns, so that one
+// K = 128 fp8 row pairs with the weight stage [e4m3(S w) | e4m3(S w - fp16(S w))]:
+//     a w ~= a16 w16 + e5m2(a_lo) e4m3(w) + e4m3(a) e4m3(w_lo)
+__device__ __forceinline__ void tc2_store_a16_f16f8(uint32_t tmem_a, int c0, const float (&h)[16]) {
+  uint32_t hi[8], lo8[4], a8[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float x0 = h[4 * q], x1 = h[4 * q + 1], x2 = h[4 * q + 2], x3 = h[4 * q + 3];
+    hi[2 * q] = ptx::pack_f16x2_pinned(x0, x1);
+    hi[2 * q + 1] = ptx::pack_f16x2_pinned(x2, x3);
+    const float2 r01 = ptx::f16x2_residual(hi[2 * q], x0, x1);
+    const float2 r23 = ptx::f16x2_residual(hi[2 * q + 1], x2, x3);
+    lo8[q] = ptx::pack_e5m2x4(r01.x, r01.y, r23.x, r23.y);
+    a8[q] = ptx::pack_e4m3x4(x0, x1, x2, x3);
+  }
+  const int slab = c0 >> 6, k0 = c0 & 63;
+  ptx::tmem_st_32x32b_x8(tmem_a + c0 / 2, hi);
+  ptx::tmem_st_32x32b_x4(tmem_a + 64 + slab * 32 + k0 / 4, lo8);
+  ptx::tmem_st_32x32b_x4(tmem_a + 64 + slab * 32 + 16 + k0 / 4, a8);
+}
+
 template <int PREC, bool PACKED_MATH = true>
 __device__ __forceinline__ void tc2_store_a(uint32_t tmem_a, int c0, const float (&h)[32]) {
+  if constexpr (PREC == CNF_PREC_F16F8) {
+    float h0[16], h1[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { h0[j] = h[j]; h1[j] = h[16 + j]; }
+    tc2_store_a16_f16f8(tmem_a, c0, h0);
+    tc2_store_a16_f16f8(tmem_a, c0 + 16, h1);
+    return;
+  }
   constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
   uint32_t hi[16], lo[16];
 #pragma unroll
@@ -77,6 +110,10 @@ __device__ __forceinline__ void tc2_store_a(uint32_t tmem_a, int c0, const float
 // subtractions (its register pressure turns the 64-bit register pairs into spills: measured 6% slower).
 template <int PREC, bool PACKED_MATH = true>
 __device__ __forceinline__ void tc2_store_a16(uint32_t tmem_a, int c0, const float (&h)[16]) {
+  if constexpr (PREC == CNF_PREC_F16F8) {
+    tc2_store_a16_f16f8(tmem_a, c0, h);
+    return;
+  }
   constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
   uint32_t hi[8], lo[8];
 #pragma unroll
@@ -115,14 +152,15 @@ template <int PREC, bool LAST, bool STASH, typename HalfHook = Tc2NoHook>
 __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tmem_a, int hf,
                                                  const float* __restrict__ sbuf, const float* __restrict__ w_out_s,
                                                  int cout, float (&y)[4], __half* stash_l, uint64_t* a_half,
-                                                 uint64_t* a_full, HalfHook on_half = HalfHook()) {
+                                                 uint64_t* a_full, float inv = 1.f, HalfHook on_half = HalfHook()) {
+  constexpr bool SCALED = (PREC == CNF_PREC_F16F8);
   uint32_t v[2][16];
   float hcur[16], hnext[16];
   ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, 0), v[0]);
   ptx::tmem_wait_ld();
   ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, 1), v[1]);
-  tc_sines16<STASH>(v[0], sbuf + tc2_group_col(hf, 0), hnext,
-                             STASH ? stash_l + (size_t)tc2_group_col(hf, 0) * kTileM : nullptr);
+  tc_sines16<STASH, SCALED>(v[0], sbuf + tc2_group_col(hf, 0), hnext,
+                            STASH ? stash_l + (size_t)tc2_group_col(hf, 0) * kTileM : nullptr, inv);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int c0 = tc2_group_col(hf, c);
@@ -131,7 +169,7 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
     if (c + 1 < 4) {
       const int c1 = tc2_group_col(hf, c + 1);
       ptx::tmem_wait_ld();
-      tc_sines16<STASH>(v[(c + 1) & 1], sbuf + c1, hnext, STASH ? stash_l + (size_t)c1 * kTileM : nullptr);
+      tc_sines16<STASH, SCALED>(v[(c + 1) & 1], sbuf + c1, hnext, STASH ? stash_l + (size_t)c1 * kTileM : nullptr, inv);
       if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, c + 2), v[c & 1]);
     }
     if (!LAST) {
@@ -188,9 +226,13 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
   constexpr int pack_rows = PACKED ? 1 : 0;
   constexpr int H = kTc2H;
   constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
-  constexpr int kParts = kSplit ? 2 : 1;
-  constexpr int kSPL = (H / kSlabK) * kParts;  // stages per layer: 4 (split) or 2
+  constexpr bool kF8 = (PREC == CNF_PREC_F16F8);
+  constexpr int kParts = (kSplit || kF8) ? 2 : 1;
+  constexpr int kSPL = (H / kSlabK) * kParts;  // stages per layer: 4 (bf16 hi/lo, or fp16 + fp8 stage) or 2 (fp16)
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, H);
+  // f16f8: the fp8 stage's first two K=32 MMAs multiply e5m2(a_lo) by e4m3(S w), the last two e4m3(a) by e4m3(S w_lo)
+  [[maybe_unused]] constexpr uint32_t kIdescF8Lo = ptx::make_idesc_f8(ptx::kF8E5M2, ptx::kF8E4M3, kTileM, H);
+  [[maybe_unused]] constexpr uint32_t kIdescF8Hi = ptx::make_idesc_f8(ptx::kF8E4M3, ptx::kF8E4M3, kTileM, H);
   constexpr int kMmaWarp = kTc2EpiWarps;  // warps kMmaWarp, kMmaWarp+1: MMA issuers of slot 0, 1; then the producer
 
   extern __shared__ uint8_t smem_raw[];
@@ -223,6 +265,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
     const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
     for (int i = threadIdx.x; i < H * cin; i += kTc2Threads) tail->w_first_s[i] = w_first[i];
     for (int i = threadIdx.x; i < cout * H; i += kTc2Threads) tail->w_out_s[i] = w_out[i];
+    if (kF8) {
+      const float* sc = reinterpret_cast<const float*>(packed + lay.tc_scale);
+      for (int i = threadIdx.x; i < nl && i < kTc2MaxLayers; i += kTc2Threads) tail->inv_scale[i] = sc[i];
+    }
   }
   if (warp == kMmaWarp) {
     ptx::tmem_alloc(&tail->tmem_base, 512);
@@ -330,25 +376,26 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         layer_prologue(l);
         cur_layer = l;
         // two call sites so that each sees a pointer of known address space (ld.shared vs ld.global, not generic)
+        const float inv = kF8 ? tail->inv_scale[l - 1] : 1.f;
         if (!PACKED)
-          tc2_hidden_layer<PREC, false, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][l & 1], tail->w_out_s, cout,
-                                                       y, STASH ? st_row + (size_t)l * H * kTileM : nullptr,
-                                                       &tail->a_half[g], &tail->a_full[g], half_hook);
+          tc2_hidden_layer<PREC, false, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][l & 1], tail->w_out_s, cout, y,
+                                               STASH ? st_row + (size_t)l * H * kTileM : nullptr, &tail->a_half[g],
+                                               &tail->a_full[g], inv, half_hook);
         else
           tc2_hidden_layer<PREC, false, STASH>(lane_base, tmem_a, hf, sh + (size_t)l * H, tail->w_out_s, cout, y,
-                                                       STASH ? st_row + (size_t)l * H * kTileM : nullptr,
-                                                       &tail->a_half[g], &tail->a_full[g], half_hook);
+                                               STASH ? st_row + (size_t)l * H * kTileM : nullptr, &tail->a_half[g],
+                                               &tail->a_full[g], inv, half_hook);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
       }
       {
         layer_prologue(nl);
+        const float inv = kF8 ? tail->inv_scale[nl - 1] : 1.f;
         if (!PACKED)
-          tc2_hidden_layer<PREC, true, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][nl & 1], tail->w_out_s, cout,
-                                                      y, STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr,
-                                                      nullptr);
+          tc2_hidden_layer<PREC, true, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][nl & 1], tail->w_out_s, cout, y,
+                                              STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr, nullptr, inv);
         else
           tc2_hidden_layer<PREC, true, STASH>(lane_base, tmem_a, hf, sh + (size_t)nl * H, tail->w_out_s, cout, y,
-                                                      STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr, nullptr);
+                                              STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr, nullptr, inv);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + nl);
       }
       // ---- head: combine the two column halves, 12-byte store per point
@@ -453,6 +500,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
                   if (part == 0) {
                     ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (uint32_t)((half | kk) != 0));
                     if (kSplit) ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
+                  } else if (kF8) {  // 32 8-bit K elements = 8 packed columns of this K slab's fp8 operand
+                    ptx::umma_f8_ts(tmem_d, tmem_a + 64 + half * 32 + kk * 8, b + 2 * kk,
+                                    kk < 2 ? kIdescF8Lo : kIdescF8Hi, 1u);
                   } else {
                     ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
                   }
@@ -476,7 +526,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
   } else if (warp == kMmaWarp + 2) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      const uint8_t* wsrc = packed + (kSplit ? lay.tc_fwd_x3 : lay.tc_fwd_h);
+      const uint8_t* wsrc = packed + (kSplit ? lay.tc_fwd_x3 : kF8 ? lay.tc_fwd_f8 : lay.tc_fwd_h);
       int slot = 0;
       uint32_t phase = 0;
       for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {

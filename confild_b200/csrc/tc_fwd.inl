@@ -40,7 +40,11 @@ int dispatch_stash(const FwdArgs& a) {
 
 int CNF_TU_NAME(const FwdArgs& a) {
   switch (a.d.H) {
-    case 128: return dispatch_stash<128>(a);
+    case 128:
+      if constexpr (CNF_TU_PREC == CNF_PREC_F16F8)
+        return fail(CNF_ERR_UNSUPPORTED, "f16f8 at H=128 runs on the TMEM-resident kernels only (CNF_TC2=0 excludes it)");
+      else
+        return dispatch_stash<128>(a);
     case 256: return dispatch_stash<256>(a);
     case 384: return dispatch_stash<384>(a);
   }

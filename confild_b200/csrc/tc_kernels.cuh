@@ -33,7 +33,10 @@ constexpr int kTcTailBytes = 384;  // shared-memory area reserved for TcSmemTail
 template <int H, int PREC>
 struct TcCfg {
   static constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
-  static constexpr int kParts = kSplit ? 2 : 1;
+  // f16f8: part 0 = fp16 operands, part 1 = the fp8 operands (A: [e5m2(a - fp16 a) | e4m3(a)], B: [e4m3(S w) |
+  // e4m3(S w - fp16(S w))] per K slab, 128 bytes per row -- the same bytes as a 16-bit slab, so every size below holds)
+  static constexpr bool kF8 = (PREC == CNF_PREC_F16F8);
+  static constexpr int kParts = (kSplit || kF8) ? 2 : 1;
   static constexpr int kSlabs = H / kSlabK;
   static constexpr int kNBlocks = H / kStageRows;
   // The first kATmemBlocks 128-column blocks of the A operand live in the TMEM columns the accumulator leaves free
@@ -55,7 +58,10 @@ struct TcCfg {
   static constexpr bool kBlockPipe = (H == 256 || H == 384);
   static constexpr uint32_t kTmemCols = (H + kATmemCols) <= 256 ? 256u : 512u;
   static constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, kStageRows);
+  static constexpr uint32_t kIdescF8Lo = ptx::make_idesc_f8(ptx::kF8E5M2, ptx::kF8E4M3, kTileM, kStageRows);
+  static constexpr uint32_t kIdescF8Hi = ptx::make_idesc_f8(ptx::kF8E4M3, ptx::kF8E4M3, kTileM, kStageRows);
   static_assert(kColsPerGroup % 16 == 0, "column groups are processed 16 columns at a time");
+  static_assert(!kF8 || kBlockPipe, "f16f8 is implemented for the block-pipelined widths (H = 256, 384) here; H = 128 has tc2");
 };
 
 struct TcSmemTail {  // lives after the A operand and the weight ring
@@ -155,6 +161,37 @@ template <int H, int PREC>
 __device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, uint32_t tmem_row, int row, int c0,
                                              const float (&h)[16]) {
   using C = TcCfg<H, PREC>;
+  if constexpr (C::kF8) {
+    uint32_t hi[8], lo8[4], a8[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x0 = h[4 * q], x1 = h[4 * q + 1], x2 = h[4 * q + 2], x3 = h[4 * q + 3];
+      hi[2 * q] = ptx::pack_f16x2(x0, x1);
+      hi[2 * q + 1] = ptx::pack_f16x2(x2, x3);
+      const float2 r01 = ptx::f16x2_residual(hi[2 * q], x0, x1);
+      const float2 r23 = ptx::f16x2_residual(hi[2 * q + 1], x2, x3);
+      lo8[q] = ptx::pack_e5m2x4(r01.x, r01.y, r23.x, r23.y);
+      a8[q] = ptx::pack_e4m3x4(x0, x1, x2, x3);
+    }
+    if (c0 < C::kATmemCols) {  // TMEM-resident 128-column block: fp16 in [0,64), fp8 operand of slab s in [64 + 32s, +32)
+      const uint32_t tb = tmem_row + H + (c0 / 128) * 128;
+      const int cb = c0 % 128, slab = cb >> 6, k0 = cb & 63;
+      ptx::tmem_st_32x32b_x8(tb + cb / 2, hi);
+      ptx::tmem_st_32x32b_x4(tb + 64 + slab * 32 + k0 / 4, lo8);
+      ptx::tmem_st_32x32b_x4(tb + 64 + slab * 32 + 16 + k0 / 4, a8);
+      return;
+    }
+    const int cs = c0 - C::kATmemCols;
+    uint8_t* rowp = a_smem + (cs / kSlabK) * (kTileM * 128) + row * 128;
+    const uint32_t k0 = cs % kSlabK;
+    const uint32_t x = row & 7;
+    *reinterpret_cast<uint4*>(rowp + (((k0 / 8) ^ x) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(rowp + (((k0 / 8 + 1) ^ x) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    uint8_t* row8 = rowp + C::kAPartBytes;  // the fp8 operand's row: 16-byte chunk k0/16 (a_lo) and 4 + k0/16 (a)
+    *reinterpret_cast<uint4*>(row8 + (((k0 / 16) ^ x) << 4)) = make_uint4(lo8[0], lo8[1], lo8[2], lo8[3]);
+    *reinterpret_cast<uint4*>(row8 + (((4 + k0 / 16) ^ x) << 4)) = make_uint4(a8[0], a8[1], a8[2], a8[3]);
+    return;
+  }
   if (c0 < C::kATmemCols) {  // this K range of the operand is TMEM-resident (warp-uniform branch)
     uint32_t hi[8], lo[8];
 #pragma unroll
@@ -241,7 +278,8 @@ __device__ __forceinline__ void tc_wait_d_full(TcSmemTail* tail, int warp, uint3
 template <int H, int PREC, bool LAST, bool STASH>
 __device__ __forceinline__ void tc_block_epilogue(int n, uint8_t* a_smem, uint32_t tmem_row, int row, int cg,
                                                   const float* __restrict__ shl, const float* __restrict__ w_out,
-                                                  int cout, float (&y)[4], __half* stash_l, TcSmemTail* tail) {
+                                                  int cout, float (&y)[4], __half* stash_l, TcSmemTail* tail,
+                                                  float inv) {
   using C = TcCfg<H, PREC>;
   const int c0 = 128 * n + 32 * cg;
   uint32_t v0[16], v1[16];
@@ -253,8 +291,8 @@ __device__ __forceinline__ void tc_block_epilogue(int n, uint8_t* a_smem, uint32
     ptx::tc_fence_before();
     ptx::mbar_arrive(&tail->d_drained[n]);
   }
-  tc_sines16<STASH>(v0, shl + c0, h0, STASH ? stash_l + (size_t)c0 * kTileM : nullptr);
-  tc_sines16<STASH>(v1, shl + c0 + 16, h1, STASH ? stash_l + (size_t)(c0 + 16) * kTileM : nullptr);
+  tc_sines16<STASH, C::kF8>(v0, shl + c0, h0, STASH ? stash_l + (size_t)c0 * kTileM : nullptr, inv);
+  tc_sines16<STASH, C::kF8>(v1, shl + c0 + 16, h1, STASH ? stash_l + (size_t)(c0 + 16) * kTileM : nullptr, inv);
   if (!LAST) {
     tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h0);
     tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0 + 16, h1);
@@ -329,7 +367,11 @@ __device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t 
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t first = (part == 0) ? (uint32_t)((ks | kk) != 0) : 1u;
-            if (a_in_tmem) {
+            if (C::kF8 && part == 1) {  // fp8 stage: K = 32 per MMA; e5m2(a_lo) x e4m3(S w), then e4m3(a) x e4m3(S w_lo)
+              const uint32_t id8 = kk < 2 ? C::kIdescF8Lo : C::kIdescF8Hi;
+              if (a_in_tmem) ptx::umma_f8_ts(dcol, tmem_d + H + (ks / 2) * 128 + 64 + (ks & 1) * 32 + kk * 8, b + 2 * kk, id8, 1u);
+              else ptx::umma_f8_ss(dcol, a_lo + 2 * kk, b + 2 * kk, id8, 1u);
+            } else if (a_in_tmem) {
               ptx::umma_f16_ts(dcol, at_hi + kk * 8, b + 2 * kk, kIdesc, first);
               if (C::kSplit && part == 0) ptx::umma_f16_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdesc, 1u);
             } else {
@@ -458,6 +500,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         const bool last = (l == nl);
         if constexpr (C::kBlockPipe) {
           __half* stl = STASH ? st_row + (size_t)l * H * kTileM : nullptr;
+          const float inv = C::kF8 ? __ldg(reinterpret_cast<const float*>(packed + lay.tc_scale) + (l - 1)) : 1.f;
           if constexpr (STAGE) {
             ptx::bar_sync(1, kTcEpiWarps * 32);  // nobody still reads the previous layer's shifts
             for (int i = threadIdx.x; i < H; i += kTcEpiWarps * 32) shift_s[i] = __ldg(shl + i);
@@ -473,14 +516,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
             // two call sites per variant so that each sees a pointer of known address space (ld.shared vs ld.global)
             if constexpr (STAGE) {
               if (!last)
-                tc_block_epilogue<H, PREC, false, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail);
+                tc_block_epilogue<H, PREC, false, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail, inv);
               else
-                tc_block_epilogue<H, PREC, true, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail);
+                tc_block_epilogue<H, PREC, true, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail, inv);
             } else {
               if (!last)
-                tc_block_epilogue<H, PREC, false, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+                tc_block_epilogue<H, PREC, false, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail, inv);
               else
-                tc_block_epilogue<H, PREC, true, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail);
+                tc_block_epilogue<H, PREC, true, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail, inv);
             }
             if (tracer) CNF_TRACE_EVENT(trole, 600 + 10 * l + n);  // epilogue of block n done
           }
@@ -605,7 +648,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
   } else {
     // ===================== weight producer =====================
     if (lane == 0) {
-      const uint8_t* wsrc = packed + (C::kSplit ? lay.tc_fwd_x3 : lay.tc_fwd_h);
+      const uint8_t* wsrc = packed + (C::kSplit ? lay.tc_fwd_x3 : C::kF8 ? lay.tc_fwd_f8 : lay.tc_fwd_h);
       int slot = 0;
       uint32_t phase = 0;
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {

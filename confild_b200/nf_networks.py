@@ -30,6 +30,8 @@ DEFAULT_W0 = 30.0  # reference: cnf/initialization.py:5
 PRECISION_NOTES = {
     "bf16x3": "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate",
     "fp16": "tcgen05 single fp16 MMA per product, fp32 accumulate",
+    "f16f8": "tcgen05 fp16 product + two fp8 (e5m2/e4m3, kind::f8f6f4) correction products = 2 MMA-equivalents per "
+             "product, fp32 accumulate",
     "fp32": "CUDA-core fp32 FMA",
 }
 

@@ -18,7 +18,7 @@ def test_reference_arm_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "cnf_decode_point_frames_per_s"
     assert d["unit"] == "point-frames/s" and d["higher_is_better"] is True and d["value"] > 0
-    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ConditionalNeuralField", "cnf", "nf_networks.pyc"))
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ConditionalNeuralField", "cnf", "nf_networks.bin"))
     assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("CNF decode case1")

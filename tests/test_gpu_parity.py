@@ -12,13 +12,14 @@ from oracle import cnf_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FWD_TOL = {"fp32": 2e-5, "bf16x3": 1e-3, "fp16": 1e-3}
+FWD_TOL = {"fp32": 2e-5, "bf16x3": 1e-3, "fp16": 1e-3, "f16f8": 1e-3}
 # The single-pass fp16 fast mode meets 1e-3 only on the narrow/shallow nets (case1, case2); on case3 (17 layers)
 # and case4 (H=384) it measures 1e-3..2e-3, so there it is held to its own documented bound, not the contract.
 FP16_FWD_BOUND = {"case1": 1e-3, "case2": 1e-3, "case3": 3e-3, "case4": 3e-3}
-BWD_TOL = {"fp32": 1e-4, "bf16x3": 1e-2, "fp16": 1e-2}
+BWD_TOL = {"fp32": 1e-4, "bf16x3": 1e-2, "fp16": 1e-2, "f16f8": 1e-2}
 # what the implementation is expected to reach (regression guard, tighter than the contract)
-FWD_EXPECT = {"fp32": 2e-5, "bf16x3": 1e-4, "fp16": 1e-3}
+# f16f8 (fp16 product + two fp8 correction products) is held to 2e-4: >= 5x inside the contract on every recipe shape
+FWD_EXPECT = {"fp32": 2e-5, "bf16x3": 1e-4, "fp16": 1e-3, "f16f8": 2e-4}
 
 
 @pytest.fixture
@@ -40,7 +41,7 @@ def make_model(dims, sd, precision):
 
 def precisions_for(dims):
     d = _native.dims(dims[0], dims[1], dims[4], dims[3], dims[2])
-    return ["fp32", "bf16x3", "fp16"] if _native.tc_supported(d) else ["fp32"]
+    return ["fp32", "bf16x3", "fp16", "f16f8"] if _native.tc_supported(d) else ["fp32"]
 
 
 def test_raw_c_abi_forward_backward():
@@ -461,7 +462,7 @@ def test_forward_is_bitwise_reproducible_and_grad_mode_invariant(case, T, P):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dims", [(2, 16, 3, 1, 128), (2, 16, 3, 2, 128), (3, 8, 2, 1, 256), (2, 8, 4, 2, 384)])
-@pytest.mark.parametrize("prec", ["bf16x3", "fp16"])
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16", "f16f8"])
 def test_shallow_networks_forward_and_gradient(dims, prec):
     """nl = 1 / 2: the issue schedules (half-layer, block pipeline) start and end inside one or two hidden layers;
     odd tile counts leave the second tile slot of the H=128 kernels idle in the last pair."""

@@ -46,3 +46,12 @@ for l in (3, 4, 5):
         for w in range(8 * g, 8 * g + 8, 4):
             d = nth(ev[4 + w], 300 + l, TILE); e = nth(ev[4 + w], 400 + l, TILE); hh = nth(ev[4 + w], 350 + l, TILE)
             print(f"    warp {w:2d} (hf={(w // 4) % 2} wq={w % 4}): d_full seen {d} (+{d - last}), a_half arrived {hh} (+{hh - d}), epilogue done {e} (E={e - d})")
+
+# steady-state layer period of the pair: time between successive layers' (slot 0, half 0) issue events
+ts = [nth(ev[2], 3000 + l, TILE) for l in range(2, 10)]
+print("slot0 half0 issued at", ts, "period", [b - a for a, b in zip(ts, ts[1:])])
+for g in (0, 1):
+    w = 8 * g
+    ds = [nth(ev[4 + w], 300 + l, TILE) for l in range(2, 10)]
+    es = [nth(ev[4 + w], 400 + l, TILE) for l in range(2, 10)]
+    print(f"slot {g} warp {w}: d_full seen", ds, " E durations", [e - d for d, e in zip(ds, es)], " gap E_done->next d_full", [d2 - e for e, d2 in zip(es, ds[1:])])
