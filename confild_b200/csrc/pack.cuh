@@ -116,6 +116,11 @@ __global__ void __launch_bounds__(256) pack_scale_kernel(cnf_dims d, const float
   }
 }
 
+// The kernels build their e5m2 activation operands by TRUNCATING fp16 words to their high byte (2 mantissa bits); for a
+// uniformly distributed mantissa the least-squares factor that re-centres the truncated value is 1.0873, folded here
+// into the fp8 weight images that multiply those operands (scripts/emulate_precision.py: same error as rounding).
+constexpr float kF8TruncComp = 1.0873f;
+
 // f16f8 precision, step 2: the stage images.  One thread per weight element.
 __global__ void pack_tc_f8_kernel(cnf_dims d, const float* __restrict__ params, float w0, uint8_t* __restrict__ packed) {
   const PackedLayout lay = make_layout(d);
@@ -137,8 +142,8 @@ __global__ void pack_tc_f8_kernel(cnf_dims d, const float* __restrict__ params, 
     uint8_t* st16 = base + (l * spl + (ks * 2 + 0) * nblocks + nb) * (size_t)kStageBytes;
     uint8_t* st8 = base + (l * spl + (ks * 2 + 1) * nblocks + nb) * (size_t)kStageBytes;
     *reinterpret_cast<uint16_t*>(st16 + sw128_offset(r, kk)) = __half_as_ushort(h);
-    st8[sw128_byte_offset(r, kk)] = (uint8_t)__nv_cvt_float_to_fp8(w, __NV_SATFINITE, __NV_E4M3);
-    st8[sw128_byte_offset(r, 64 + kk)] = (uint8_t)__nv_cvt_float_to_fp8(lo, __NV_SATFINITE, __NV_E4M3);
+    st8[sw128_byte_offset(r, kk)] = (uint8_t)__nv_cvt_float_to_fp8(kF8TruncComp * w, __NV_SATFINITE, __NV_E4M3);
+    st8[sw128_byte_offset(r, 64 + kk)] = (uint8_t)__nv_cvt_float_to_fp8(kF8TruncComp * lo, __NV_SATFINITE, __NV_E4M3);
   }
 }
 

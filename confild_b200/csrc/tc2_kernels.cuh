@@ -51,23 +51,10 @@ __host__ __device__ constexpr size_t tc2_smem_bytes(int num_stages) {
   return 1024 + (size_t)num_stages * kStageBytes + sizeof(Tc2SmemTail);
 }
 
-// f16f8 operand of 16 activations (columns c0..c0+15 of this thread's row, c0 % 16 == 0), TMEM columns relative to the
-// slot's A area (128 columns): fp16 copy in [0,64) as for the other precisions; the 8-bit operand of K slab s = c0/64 in
-// [64 + 32s, +32): bytes [0,64) = e5m2(a - fp16(a)) and bytes [64,128) = e4m3(a) of the slab's 64 columns, so that one
-// K = 128 fp8 row pairs with the weight stage [e4m3(S w) | e4m3(S w - fp16(S w))]:
-//     a w ~= a16 w16 + e5m2(a_lo) e4m3(w) + e4m3(a) e4m3(w_lo)
+// f16f8: see f16f8_operands16 (tc_common.cuh) for the operand formats.
 __device__ __forceinline__ void tc2_store_a16_f16f8(uint32_t tmem_a, int c0, const float (&h)[16]) {
   uint32_t hi[8], lo8[4], a8[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float x0 = h[4 * q], x1 = h[4 * q + 1], x2 = h[4 * q + 2], x3 = h[4 * q + 3];
-    hi[2 * q] = ptx::pack_f16x2_pinned(x0, x1);
-    hi[2 * q + 1] = ptx::pack_f16x2_pinned(x2, x3);
-    const float2 r01 = ptx::f16x2_residual(hi[2 * q], x0, x1);
-    const float2 r23 = ptx::f16x2_residual(hi[2 * q + 1], x2, x3);
-    lo8[q] = ptx::pack_e5m2x4(r01.x, r01.y, r23.x, r23.y);
-    a8[q] = ptx::pack_e4m3x4(x0, x1, x2, x3);
-  }
+  f16f8_operands16(h, hi, lo8, a8);
   const int slab = c0 >> 6, k0 = c0 & 63;
   ptx::tmem_st_32x32b_x8(tmem_a + c0 / 2, hi);
   ptx::tmem_st_32x32b_x4(tmem_a + 64 + slab * 32 + k0 / 4, lo8);
@@ -230,9 +217,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
   constexpr int kParts = (kSplit || kF8) ? 2 : 1;
   constexpr int kSPL = (H / kSlabK) * kParts;  // stages per layer: 4 (bf16 hi/lo, or fp16 + fp8 stage) or 2 (fp16)
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, H);
-  // f16f8: the fp8 stage's first two K=32 MMAs multiply e5m2(a_lo) by e4m3(S w), the last two e4m3(a) by e4m3(S w_lo)
-  [[maybe_unused]] constexpr uint32_t kIdescF8Lo = ptx::make_idesc_f8(ptx::kF8E5M2, ptx::kF8E4M3, kTileM, H);
-  [[maybe_unused]] constexpr uint32_t kIdescF8Hi = ptx::make_idesc_f8(ptx::kF8E4M3, ptx::kF8E4M3, kTileM, H);
+  // f16f8: the fp8 stage's first two K=32 MMAs multiply e5m2(a_lo) by e4m3(S w), the last two e5m2(a) by e4m3(S w_lo)
+  [[maybe_unused]] constexpr uint32_t kIdescF8 = ptx::make_idesc_f8(ptx::kF8E5M2, ptx::kF8E4M3, kTileM, H);
   constexpr int kMmaWarp = kTc2EpiWarps;  // warps kMmaWarp, kMmaWarp+1: MMA issuers of slot 0, 1; then the producer
 
   extern __shared__ uint8_t smem_raw[];
@@ -501,8 +487,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
                     ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (uint32_t)((half | kk) != 0));
                     if (kSplit) ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
                   } else if (kF8) {  // 32 8-bit K elements = 8 packed columns of this K slab's fp8 operand
-                    ptx::umma_f8_ts(tmem_d, tmem_a + 64 + half * 32 + kk * 8, b + 2 * kk,
-                                    kk < 2 ? kIdescF8Lo : kIdescF8Hi, 1u);
+                    ptx::umma_f8_ts(tmem_d, tmem_a + 64 + half * 32 + kk * 8, b + 2 * kk, kIdescF8, 1u);
                   } else {
                     ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
                   }

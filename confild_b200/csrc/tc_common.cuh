@@ -133,6 +133,29 @@ __device__ __forceinline__ void tc_sines16(const uint32_t (&v)[16], const float*
   if (STASH) tc_stash16(stash_dst, cs);  // stash_dst = st_row + (l*H + c)*128, always a valid slot
 }
 
+// f16f8 operand of 16 activations (columns c0..c0+15 of this thread's row, c0 % 16 == 0), TMEM columns relative to the
+// slot's A area (128 columns): fp16 copy in [0,64) as for the other precisions; the 8-bit operand of K slab s = c0/64 in
+// [64 + 32s, +32): bytes [0,64) = e5m2(a - fp16(a)) and bytes [64,128) = e5m2(a) of the slab's 64 columns, so that one
+// K = 128 fp8 row pairs with the weight stage [e4m3(c S w) | e4m3(c S (w - fp16 w))]:
+//     a w ~= a16 w16 + e5m2(a_lo) e4m3(w) + e5m2(a) e4m3(w_lo)
+// The e5m2 values are the HIGH BYTES of fp16 words (same sign / exponent layout, mantissa truncated to 2 bits): one
+// PRMT per four values on the ALU pipe.  cvt.rn.satfinite.e4m3x2 / e5m2x2 would round to nearest but run at MUFU-class
+// throughput and doubled the epilogue's XU load (measured: slot epilogue 1.85 k -> 2.5 k clk); the mean truncation loss
+// is instead folded into the packed fp8 weights as the constant kF8TruncComp (pack.cuh), which leaves the same
+// zero-mean error as round-to-nearest (scripts/emulate_precision.py).
+__device__ __forceinline__ void f16f8_operands16(const float (&h)[16], uint32_t (&hi)[8], uint32_t (&lo8)[4],
+                                                 uint32_t (&a8)[4]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float x0 = h[4 * q], x1 = h[4 * q + 1], x2 = h[4 * q + 2], x3 = h[4 * q + 3];
+    hi[2 * q] = ptx::pack_f16x2_pinned(x0, x1);
+    hi[2 * q + 1] = ptx::pack_f16x2_pinned(x2, x3);
+    const float2 r01 = ptx::f16x2_residual(hi[2 * q], x0, x1);
+    const float2 r23 = ptx::f16x2_residual(hi[2 * q + 1], x2, x3);
+    lo8[q] = __byte_perm(ptx::pack_f16x2_pinned(r01.x, r01.y), ptx::pack_f16x2_pinned(r23.x, r23.y), 0x7531);
+    a8[q] = __byte_perm(hi[2 * q], hi[2 * q + 1], 0x7531);
+  }
+}
 #ifdef CNF_TRACE
 #define CNF_CHECK(cond, what, a, b)                                                                             \
   do {                                                                                                          \

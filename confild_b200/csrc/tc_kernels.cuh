@@ -33,8 +33,9 @@ constexpr int kTcTailBytes = 384;  // shared-memory area reserved for TcSmemTail
 template <int H, int PREC>
 struct TcCfg {
   static constexpr bool kSplit = (PREC == CNF_PREC_BF16X3);
-  // f16f8: part 0 = fp16 operands, part 1 = the fp8 operands (A: [e5m2(a - fp16 a) | e4m3(a)], B: [e4m3(S w) |
-  // e4m3(S w - fp16(S w))] per K slab, 128 bytes per row -- the same bytes as a 16-bit slab, so every size below holds)
+  // f16f8: part 0 = fp16 operands, part 1 = the fp8 operands (A: [e5m2(a - fp16 a) | e5m2(a)], B: [e4m3(c S w) |
+  // e4m3(c S (w - fp16 w))] per K slab, 128 bytes per row -- the same bytes as a 16-bit slab, so every size below holds;
+  // see f16f8_operands16 in tc_common.cuh)
   static constexpr bool kF8 = (PREC == CNF_PREC_F16F8);
   static constexpr int kParts = (kSplit || kF8) ? 2 : 1;
   static constexpr int kSlabs = H / kSlabK;
@@ -58,8 +59,7 @@ struct TcCfg {
   static constexpr bool kBlockPipe = (H == 256 || H == 384);
   static constexpr uint32_t kTmemCols = (H + kATmemCols) <= 256 ? 256u : 512u;
   static constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, kStageRows);
-  static constexpr uint32_t kIdescF8Lo = ptx::make_idesc_f8(ptx::kF8E5M2, ptx::kF8E4M3, kTileM, kStageRows);
-  static constexpr uint32_t kIdescF8Hi = ptx::make_idesc_f8(ptx::kF8E4M3, ptx::kF8E4M3, kTileM, kStageRows);
+  static constexpr uint32_t kIdescF8 = ptx::make_idesc_f8(ptx::kF8E5M2, ptx::kF8E4M3, kTileM, kStageRows);
   static_assert(kColsPerGroup % 16 == 0, "column groups are processed 16 columns at a time");
   static_assert(!kF8 || kBlockPipe, "f16f8 is implemented for the block-pipelined widths (H = 256, 384) here; H = 128 has tc2");
 };
@@ -163,16 +163,7 @@ __device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, uint32_t tmem_row,
   using C = TcCfg<H, PREC>;
   if constexpr (C::kF8) {
     uint32_t hi[8], lo8[4], a8[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float x0 = h[4 * q], x1 = h[4 * q + 1], x2 = h[4 * q + 2], x3 = h[4 * q + 3];
-      hi[2 * q] = ptx::pack_f16x2(x0, x1);
-      hi[2 * q + 1] = ptx::pack_f16x2(x2, x3);
-      const float2 r01 = ptx::f16x2_residual(hi[2 * q], x0, x1);
-      const float2 r23 = ptx::f16x2_residual(hi[2 * q + 1], x2, x3);
-      lo8[q] = ptx::pack_e5m2x4(r01.x, r01.y, r23.x, r23.y);
-      a8[q] = ptx::pack_e4m3x4(x0, x1, x2, x3);
-    }
+    f16f8_operands16(h, hi, lo8, a8);
     if (c0 < C::kATmemCols) {  // TMEM-resident 128-column block: fp16 in [0,64), fp8 operand of slab s in [64 + 32s, +32)
       const uint32_t tb = tmem_row + H + (c0 / 128) * 128;
       const int cb = c0 % 128, slab = cb >> 6, k0 = cb & 63;
@@ -367,8 +358,8 @@ __device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t 
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint32_t first = (part == 0) ? (uint32_t)((ks | kk) != 0) : 1u;
-            if (C::kF8 && part == 1) {  // fp8 stage: K = 32 per MMA; e5m2(a_lo) x e4m3(S w), then e4m3(a) x e4m3(S w_lo)
-              const uint32_t id8 = kk < 2 ? C::kIdescF8Lo : C::kIdescF8Hi;
+            if (C::kF8 && part == 1) {  // fp8 stage: K = 32 per MMA; e5m2(a_lo) x e4m3(S w), then e5m2(a) x e4m3(S w_lo)
+              const uint32_t id8 = C::kIdescF8;
               if (a_in_tmem) ptx::umma_f8_ts(dcol, tmem_d + H + (ks / 2) * 128 + 64 + (ks & 1) * 32 + kk * 8, b + 2 * kk, id8, 1u);
               else ptx::umma_f8_ss(dcol, a_lo + 2 * kk, b + 2 * kk, id8, 1u);
             } else if (a_in_tmem) {

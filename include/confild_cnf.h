@@ -48,7 +48,7 @@ extern "C" {
 #define CNF_PREC_BF16X3 1 /* tcgen05, bf16 hi/lo split, 3 MMAs per product (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo) */
 #define CNF_PREC_FP16 2   /* tcgen05, single fp16 MMA per product (fast mode; error ~4e-4..1e-3)          */
 #define CNF_PREC_F16F8 3  /* tcgen05, fp16 product + two fp8 (kind::f8f6f4) correction products at twice the fp16 rate:
-                           *   a*w ~= f16(a)*f16(Sw) + e5m2(a - f16 a)*e4m3(Sw) + e4m3(a)*e4m3(Sw - f16(Sw)),  S = 2^n per layer
+                           *   a*w ~= f16(a)*f16(Sw) + e5m2(a - f16 a)*e4m3(Sw) + e5m2(a)*e4m3(Sw - f16(Sw)),  S = 2^n per layer
                            * = 2 MMA-equivalents per product instead of 3; forward error 2e-5..9e-5.
                            * Forward only: cnf_backward with this precision runs the bf16 hi/lo kernels on the same stash. */
 

@@ -66,3 +66,15 @@ def test_shared_cuda_runtime_no_embedded_runtime_names():
     """The library links the shared CUDA runtime: no runtime entry-point names are embedded in it."""
     data = open(build.LIB_PATH, "rb").read()
     assert b"MemcpyBatch" not in data
+
+
+def test_auto_precision_policy_resolution():
+    """precision="auto" (the default) resolves to f16f8 on the tensor-core shapes and to fp32 elsewhere."""
+    m = cb.SIRENAutodecoder_film(2, 128, 3, 10, 128)
+    assert m.precision == "auto" and m.resolved_precision == "f16f8"
+    assert cb.SIRENAutodecoder_film(3, 384, 3, 15, 384).resolved_precision == "f16f8"
+    assert cb.SIRENAutodecoder_film(2, 32, 3, 2, 64).resolved_precision == "fp32"      # H without tensor-core kernels
+    assert cb.SIRENAutodecoder_film(2, 16, 3, 70, 128).resolved_precision == "fp32"    # deeper than the scale table
+    assert cb.SIRENAutodecoder_film(2, 128, 3, 10, 128, precision="bf16x3").resolved_precision == "bf16x3"
+    with pytest.raises(ValueError):
+        cb.SIRENAutodecoder_film(2, 128, 3, 10, 128, precision="int4")._precision_code()
