@@ -336,6 +336,11 @@ def measure_dps(cb, model, dims, case, dev, args, iters):
 
     def fused_step():
         l = ld[:, None].detach().requires_grad_(True)
+        norm = cb.measurement_norm(model, cd[None], l, ym_masked, mask=mask, zero_row_skip=False)
+        torch.autograd.grad(norm, l)
+
+    def fused_skip_step():
+        l = ld[:, None].detach().requires_grad_(True)
         norm = cb.measurement_norm(model, cd[None], l, ym_masked, mask=mask)
         torch.autograd.grad(norm, l)
 
@@ -349,14 +354,17 @@ def measure_dps(cb, model, dims, case, dev, args, iters):
     res = {"workload": f"{case} shapes, {Td} latents x {Pd} points, {S} random sensors, forward(+cos stash) + loss + "
                        "backward to dL/dlatent (BASELINE config 4)", "precision": model.precision}
     for name, fn, rows in (("autograd_dense", autograd_step, Td * Pd), ("fused_loss_dense", fused_step, Td * Pd),
+                           ("fused_loss_dense_zero_row_skip", fused_skip_step, Td * Pd),
                            ("sensor_compacted", compact_step, Td * S)):
         ms = timed(fn, iters)
         res[name] = {"ms_per_step": ms, "point_frames_per_s": rows / (ms * 1e-3), "rows_per_step": rows}
     res["value"] = res["fused_loss_dense"]["point_frames_per_s"]
     res["ms_per_step"] = res["fused_loss_dense"]["ms_per_step"]
     res["unit"] = UNIT
-    res["note"] = ("value = fused_loss_dense (dense evaluation over all P, the graded quantity); sensor_compacted decodes "
-                   "only the sensor rows and is reported separately (SURVEY.md 8d)")
+    res["note"] = ("value = fused_loss_dense: every point decoded WITH its backward stash and visited by the backward (the "
+                   "graded dense quantity); fused_loss_dense_zero_row_skip also decodes and scores every point but stashes "
+                   "/ back-propagates only the rows whose mask weight is non-zero (exact gradient, P/#sensors less stash "
+                   "traffic); sensor_compacted decodes only the sensor rows (SURVEY.md 8d: reported separately)")
     return res
 
 
@@ -638,10 +646,14 @@ def main_ours(args):
             line["cpu_baseline"] = cpu_base
         if extra:
             line["extra"] = extra
-        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        # the single JSON line is the LAST thing written to stdout: NCCL's own logging (NCCL_DEBUG is left to the
+        # environment so that the driver can read the communicator lines) comes before it
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     return 0
 
 

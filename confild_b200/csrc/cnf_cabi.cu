@@ -62,6 +62,7 @@ Knobs& mutable_knobs() {
     k.tc2 = env_int("CNF_TC2", 1);
     k.stages = env_int("CNF_TC_STAGES", 0);
     k.packed = env_int("CNF_TC_PACKED", -1);
+    k.cluster = env_int("CNF_TC_CLUSTER", 1);
   });
   return k;
 }
@@ -72,6 +73,7 @@ int set_knob(const char* name, int value) {
   if (!strcmp(name, "CNF_TC2")) k.tc2 = value;
   else if (!strcmp(name, "CNF_TC_STAGES")) k.stages = value;
   else if (!strcmp(name, "CNF_TC_PACKED")) k.packed = value;
+  else if (!strcmp(name, "CNF_TC_CLUSTER")) k.cluster = value;
   else return fail(CNF_ERR_INVALID_ARGUMENT, "unknown debug knob %s", name);
   return CNF_OK;
 }

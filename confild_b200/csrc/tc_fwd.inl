@@ -8,7 +8,7 @@ namespace {
 
 template <int H, int PREC, bool STASH>
 int launch_tc_forward(const FwdArgs& a) {
-  static std::atomic<size_t> smem_set[2][kMaxDevices];
+  static std::atomic<size_t> smem_set[4][kMaxDevices];
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   const int pack_rows = use_packed(a.P);
@@ -22,6 +22,32 @@ int launch_tc_forward(const FwdArgs& a) {
   // frame-aligned tiles of the block-pipelined kernels stage the layer's FiLM shifts in shared memory
   constexpr bool kCanStage = TcCfg<H, PREC>::kBlockPipe;
   const bool stage = kCanStage && !pack_rows;
+  // CTA pairs that share every weight stage (multicast halves): worth it once there are at least two tiles per SM pair
+  constexpr bool kCanCluster = TcCfg<H, PREC>::kBlockPipe;
+  const bool cluster = kCanCluster && knobs().cluster != 0 && tiles >= 2;
+  if (cluster) {
+    auto kern = stage ? tc_forward_kernel<H, PREC, STASH, kCanStage, kCanCluster>
+                      : tc_forward_kernel<H, PREC, STASH, false, kCanCluster>;
+    if (int rc = ensure_smem(kern, plan.smem, di.device, smem_set[2 + (stage ? 1 : 0)])) return rc;
+    int64_t grid = (tiles + 1) & ~(int64_t)1;
+    const int64_t cap = di.sms & ~1;
+    if (grid > cap) grid = cap;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = a.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CNF_CUDA(cudaLaunchKernelEx(&cfg, kern, a.d, a.packed, a.coords, a.coord_frame_stride, a.shift, a.outs,
+                                reinterpret_cast<__half*>(a.stash), a.loss, a.T, a.P, plan.stages, pack_rows));
+    return CNF_OK;
+  }
   auto kern = stage ? tc_forward_kernel<H, PREC, STASH, kCanStage> : tc_forward_kernel<H, PREC, STASH, false>;
   if (int rc = ensure_smem(kern, plan.smem, di.device, smem_set[stage ? 1 : 0])) return rc;
   kern<<<(unsigned)plan.grid, kTcThreads, plan.smem, a.stream>>>(a.d, a.packed, a.coords, a.coord_frame_stride, a.shift,

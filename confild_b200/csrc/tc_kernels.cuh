@@ -225,13 +225,13 @@ __device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, uint32_t tmem_row,
 }
 
 // Common prologue: barriers, TMEM allocation.  Returns the TMEM base.
-template <int H, int PREC>
+template <int H, int PREC, bool CLUSTER = false>
 __device__ __forceinline__ uint32_t tc_setup(TcSmemTail* tail, int num_stages, int warp) {
   using C = TcCfg<H, PREC>;
   if (threadIdx.x == 0) {
     for (int s = 0; s < num_stages; ++s) {
       ptx::mbar_init(&tail->b_full[s], 1);
-      ptx::mbar_init(&tail->b_empty[s], 1);
+      ptx::mbar_init(&tail->b_empty[s], CLUSTER ? 2 : 1);  // cluster: released by the issuers of both CTAs
     }
     ptx::mbar_init(&tail->a_full, kTcEpiWarps * 32);
     ptx::mbar_init(&tail->d_full, 1);
@@ -249,6 +249,7 @@ __device__ __forceinline__ uint32_t tc_setup(TcSmemTail* tail, int num_stages, i
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CLUSTER) ptx::cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
   ptx::tc_fence_after();
   return tail->tmem_base;
 }
@@ -313,83 +314,96 @@ __device__ __forceinline__ void tc_block_epilogue(int n, uint8_t* a_smem, uint32
   }
 }
 
-// Issuer warp n: the quadrants Q(n, 0..NB-1) of one hidden layer (accumulator block n, N=128 MMAs), called as a whole
+// Issuer warp n: the issue episodes (block n, K slab 0..kSlabs-1) of one hidden layer (N=128 MMAs), called as a whole
 // converged warp.  The token (turn[]) goes round-robin n -> n+1, which yields the k-major order of kBlockPipe and makes
 // consecutive quadrants come from different warps (a warp that has issued MMAs is held until the tensor pipe has taken
 // them).  All quadrants of block n come from this warp, so its commit after Q(n, NB-1) covers the whole block; E_n
 // additionally relies on the tensor pipe completing MMAs in issue order (the quadrants of other blocks that read K part
 // n were issued earlier).  `stage` counts the weight stages consumed so far by ALL warps (ring position).
-template <int H, int PREC>
+template <int H, int PREC, bool CLUSTER = false>
 __device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t ring_addr, uint32_t tmem_d,
                                                TcSmemTail* tail, int num_stages, int& slot, uint32_t& phase,
                                                uint32_t& e_phase, uint32_t& turn_phase) {
   using C = TcCfg<H, PREC>;
   constexpr int NB = C::kNBlocks;
-  constexpr int kStagesPerQuad = 2 * C::kParts;  // two K slabs x (hi, lo) weight parts, row block n
+  constexpr int kP = C::kParts;  // weight stages of one issue episode: (hi, lo) / (fp16, fp8) / fp16 of one K slab, row block n
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kTileM, 128);
-  auto skip = [&](int quads) {
-    slot += quads * kStagesPerQuad;
+  // One issue EPISODE = accumulator block n x ONE K slab: all its weight stages are awaited first, then all its MMAs
+  // (12 bf16x3 / 8 f16f8 / 4 fp16) leave in a single elected-lane block with the stage releases interleaved, and the
+  // token moves on.  Episodes go round-robin over the issuer warps (block 0, 1, .., NB-1 of slab 0, then slab 1, ..), so
+  // a warp's barrier waits and descriptor set-up run under the other warps' queued MMAs; one episode per (block, slab,
+  // PART) -- the first version -- left the tensor pipe idle ~270 clk between the 4-MMA batches of a warp (100-133 clk
+  // per MMA whatever the precision).
+  auto skip = [&](int episodes) {
+    slot += episodes * kP;
     while (slot >= num_stages) { slot -= num_stages; phase ^= 1u; }
   };
   const uint32_t dcol = tmem_d + n * 128;
-  skip(n);  // quadrants Q(0..n-1, 0) of the other warps
+  skip(n);  // episodes (0..n-1, slab 0) of the other warps
 #pragma unroll 1
-  for (int k = 0; k < NB; ++k) {
-    // operands: K part k of A written; block n drained before its first quadrant overwrites it
-    ptx::mbar_wait(&tail->e_done[k], e_phase);
-    if (k == 0 && n > 0) ptx::mbar_wait(&tail->d_drained[n], e_phase);
+  for (int ks = 0; ks < C::kSlabs; ++ks) {
+    // operands: K part ks/2 of A written; block n drained before its first episode overwrites it; the slab's stages landed
+    if ((ks & 1) == 0) ptx::mbar_wait(&tail->e_done[ks >> 1], e_phase);
+    if (ks == 0 && n > 0) ptx::mbar_wait(&tail->d_drained[n], e_phase);
+    {
+      int sl = slot;
+      uint32_t ph = phase;
+#pragma unroll
+      for (int part = 0; part < kP; ++part) {
+        ptx::mbar_wait(&tail->b_full[sl], ph);
+        if (++sl >= num_stages) { sl = 0; ph ^= 1u; }
+      }
+    }
     ptx::mbar_wait(&tail->turn[n], turn_phase);
     turn_phase ^= 1u;
     ptx::tc_fence_after();
+    const bool a_in_tmem = ks < 2 * C::kATmemBlocks;
+    const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
+    const int ss = a_in_tmem ? 0 : ks - 2 * C::kATmemBlocks;
+    const uint64_t a_hi = ptx::make_desc_k_sw128(a_addr + ss * (kTileM * 128));
+    const uint64_t a_lo = ptx::make_desc_k_sw128(a_addr + C::kAPartBytes + ss * (kTileM * 128));
+    if (ptx::elect_one()) {
+      int sl = slot;
 #pragma unroll
-    for (int s2 = 0; s2 < 2; ++s2) {
-      const int ks = 2 * k + s2;
-      const bool a_in_tmem = ks < 2 * C::kATmemBlocks;
-      const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
-      const int ss = a_in_tmem ? 0 : ks - 2 * C::kATmemBlocks;
-      const uint64_t a_hi = ptx::make_desc_k_sw128(a_addr + ss * (kTileM * 128));
-      const uint64_t a_lo = ptx::make_desc_k_sw128(a_addr + C::kAPartBytes + ss * (kTileM * 128));
+      for (int part = 0; part < kP; ++part) {
+        const uint64_t b = ptx::make_desc_k_sw128(ring_addr + sl * kStageBytes);
 #pragma unroll
-      for (int part = 0; part < C::kParts; ++part) {
-        ptx::mbar_wait(&tail->b_full[slot], phase);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint32_t first = (part == 0) ? (uint32_t)((ks | kk) != 0) : 1u;
-            if (C::kF8 && part == 1) {  // fp8 stage: K = 32 per MMA; e5m2(a_lo) x e4m3(S w), then e5m2(a) x e4m3(S w_lo)
-              const uint32_t id8 = C::kIdescF8;
-              if (a_in_tmem) ptx::umma_f8_ts(dcol, tmem_d + H + (ks / 2) * 128 + 64 + (ks & 1) * 32 + kk * 8, b + 2 * kk, id8, 1u);
-              else ptx::umma_f8_ss(dcol, a_lo + 2 * kk, b + 2 * kk, id8, 1u);
-            } else if (a_in_tmem) {
-              ptx::umma_f16_ts(dcol, at_hi + kk * 8, b + 2 * kk, kIdesc, first);
-              if (C::kSplit && part == 0) ptx::umma_f16_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdesc, 1u);
-            } else {
-              ptx::umma_f16_ss(dcol, a_hi + 2 * kk, b + 2 * kk, kIdesc, first);
-              if (C::kSplit && part == 0) ptx::umma_f16_ss(dcol, a_lo + 2 * kk, b + 2 * kk, kIdesc, 1u);
-            }
-          }
-          ptx::umma_commit(&tail->b_empty[slot]);
-          if (s2 == 1 && part == C::kParts - 1) {
-            if (k == NB - 1) ptx::umma_commit(&tail->d_done[n]);
-            ptx::mbar_arrive(&tail->turn[n + 1 == NB ? 0 : n + 1]);
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t first = (part == 0) ? (uint32_t)((ks | kk) != 0) : 1u;
+          if (C::kF8 && part == 1) {  // fp8 stage: K = 32 per MMA; e5m2(a_lo) x e4m3(S w), then e5m2(a) x e4m3(S w_lo)
+            if (a_in_tmem) ptx::umma_f8_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, C::kIdescF8, 1u);
+            else ptx::umma_f8_ss(dcol, a_lo + 2 * kk, b + 2 * kk, C::kIdescF8, 1u);
+          } else if (a_in_tmem) {
+            ptx::umma_f16_ts(dcol, at_hi + kk * 8, b + 2 * kk, kIdesc, first);
+            if (C::kSplit && part == 0) ptx::umma_f16_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdesc, 1u);
+          } else {
+            ptx::umma_f16_ss(dcol, a_hi + 2 * kk, b + 2 * kk, kIdesc, first);
+            if (C::kSplit && part == 0) ptx::umma_f16_ss(dcol, a_lo + 2 * kk, b + 2 * kk, kIdesc, 1u);
           }
         }
-        __syncwarp();
-        if (++slot >= num_stages) { slot = 0; phase ^= 1u; }
+        if (CLUSTER) ptx::umma_commit_multicast(&tail->b_empty[sl], 0x3);  // the stage sits in both CTAs of the pair
+        else ptx::umma_commit(&tail->b_empty[sl]);
+        if (++sl >= num_stages) sl = 0;
       }
+      if (ks == C::kSlabs - 1) ptx::umma_commit(&tail->d_done[n]);
+      ptx::mbar_arrive(&tail->turn[n + 1 == NB ? 0 : n + 1]);
     }
-    if (k + 1 < NB) skip(NB - 1);  // the other warps' quadrants of this K part and the start of the next
+    __syncwarp();
+    skip(1);                               // this episode
+    if (ks + 1 < C::kSlabs) skip(NB - 1);  // the other warps' episodes of this slab and the start of the next
   }
-  skip(NB - 1 - n);  // quadrants Q(n+1.., NB-1)
+  skip(NB - 1 - n);  // episodes (n+1.., last slab)
   e_phase ^= 1u;
 }
 
 // ------------------------------------------------------------------ forward
 // STAGE (block pipeline, frame-aligned tiles only): the layer's FiLM shifts are staged in shared memory once per layer
 // instead of being read by every thread with warp-uniform global loads (the H=128 kernel lost 13-20 % without staging).
-template <int H, int PREC, bool STASH, bool STAGE = false>
+// CLUSTER (block pipeline only): launched as clusters of two CTAs that decode DIFFERENT tiles but stream the SAME weight
+// stages: each CTA fetches half of every 16 KiB stage and multicasts it into both CTAs' rings, so a weight byte is read
+// from L2 once per CTA PAIR (the H = 384 kernel is bound by that stream: ~30 B/clk/SM whatever the precision).  A ring
+// slot is refilled only after the issuers of BOTH CTAs have released it (b_empty counts two multicast commits).
+template <int H, int PREC, bool STASH, bool STAGE = false, bool CLUSTER = false>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
                                                                    const float* __restrict__ coords,
                                                                    int64_t coord_frame_stride,
@@ -410,7 +424,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
   const int64_t PB = (P + kTileM - 1) / kTileM;
   const int64_t tiles = tc_num_tiles(T, P, pack_rows);
   const int64_t SH = (int64_t)(nl + 1) * H;
-  const uint32_t tmem_base = tc_setup<H, PREC>(tail, num_stages, warp);
+  static_assert(!CLUSTER || C::kBlockPipe, "the CTA-pair weight multicast is implemented for the block pipeline");
+  const uint32_t tmem_base = tc_setup<H, PREC, CLUSTER>(tail, num_stages, warp);
+  // Tile walk.  Cluster: the pair (even, odd CTA) takes tiles (base, base + 1); both CTAs run the same number of
+  // iterations (they share every weight stage), an odd tile count leaves the odd CTA re-decoding the last tile with
+  // its results discarded (live == false).
+  const uint32_t crank = CLUSTER ? ptx::cluster_ctarank() : 0u;
+  const int64_t tile_first = CLUSTER ? (int64_t)(blockIdx.x - crank) : (int64_t)blockIdx.x;
+  const int64_t tile_end = CLUSTER ? ((tiles + 1) & ~(int64_t)1) : tiles;
+  auto tile_of = [&](int64_t base) { return CLUSTER ? (base + crank < tiles ? base + crank : tiles - 1) : base; };
 
   if (warp < kTcEpiWarps) {
     // ===================== activation warps =====================
@@ -433,13 +455,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     CNF_TRACE_DECL;
     const bool tracer = (lane == 0);
     [[maybe_unused]] const int trole = 4 + warp;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int64_t tbase = tile_first; tbase < tile_end; tbase += gridDim.x) {
+      const int64_t tile = tile_of(tbase);
+      const bool live = !CLUSTER || tbase + crank < tiles;
       const RowMap rm = tc_row_map(tile, row, T, P, PB, pack_rows);
       const int64_t t = rm.t, p = rm.p;
-      const bool valid = rm.valid;
+      const bool valid = rm.valid && live;
       const float* sh = shift + t * SH;
       float x[4] = {0.f, 0.f, 0.f, 0.f};
-      if (valid) {
+      if (rm.valid) {
         const float* cp = coords + t * coord_frame_stride + p * cin;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -593,7 +617,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         int64_t q0;
         int nvalid;
         tc_tile_range(tile, T, P, PB, pack_rows, q0, nvalid);
-        tc_store_tile(outs, y_stage, q0, nvalid, cout, threadIdx.x, kTcEpiWarps * 32);
+        tc_store_tile(outs, y_stage, q0, live ? nvalid : 0, cout, threadIdx.x, kTcEpiWarps * 32);
       }
       __syncwarp();
       ptx::bar_sync(1, kTcEpiWarps * 32);  // partial sums consumed before the next tile's layer 0 overwrites them
@@ -615,10 +639,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     if constexpr (C::kBlockPipe) {
       if (which < C::kNBlocks) {  // issuer warp n owns accumulator block n (see tc_issue_block)
         uint32_t turn_phase = which == 0 ? 1u : 0u;  // block 0 first (a fresh barrier passes a parity-1 wait)
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int64_t tbase = tile_first; tbase < tile_end; tbase += gridDim.x) {
           for (int l = 1; l <= nl; ++l) {
-            tc_issue_block<H, PREC>(which, a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase,
-                                    turn_phase);
+            tc_issue_block<H, PREC, CLUSTER>(which, a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase,
+                                             turn_phase);
             if (lane == 0) CNF_TRACE_EVENT(2 + which, 3000 + l);  // block `which` of layer l issued and committed
           }
         }
@@ -642,23 +666,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
       const uint8_t* wsrc = packed + (C::kSplit ? lay.tc_fwd_x3 : C::kF8 ? lay.tc_fwd_f8 : lay.tc_fwd_h);
       int slot = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      for (int64_t tbase = tile_first; tbase < tile_end; tbase += gridDim.x) {
         for (int l = 0; l < nl; ++l) {
           const uint8_t* src = wsrc + (size_t)l * C::kStagesPerLayer * kStageBytes;
           for (int s = 0; s < C::kStagesPerLayer; ++s) {
-            // image order: K slab -> part -> row block.  Block pipeline: consumed quadrant by quadrant, K part k-major
-            // then row block n, then the part's two K slabs, then hi/lo
+            // image order: K slab -> part -> row block
             int img = s;
-            if (C::kBlockPipe) {
-              constexpr int NB = C::kNBlocks, kSPQ = 2 * C::kParts;
-              const int q = s / kSPQ, r = s % kSPQ;
-              const int k = q / NB, n = q % NB, ks = 2 * k + r / C::kParts, part = r % C::kParts;
+            if (C::kBlockPipe) {  // consumed episode by episode: K slab -> row block n -> part (tc_issue_block)
+              constexpr int NB = C::kNBlocks;
+              const int e = s / C::kParts, part = s % C::kParts;
+              const int ks = e / NB, n = e % NB;
               img = (ks * C::kParts + part) * NB + n;
             }
             ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);
             ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kStageBytes);
-            ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)img * kStageBytes, kStageBytes,
-                          &tail->b_full[slot]);
+            if (CLUSTER) {  // this CTA's half of the stage, delivered to both CTAs (the peer sends the other half)
+              constexpr uint32_t kHalf = kStageBytes / 2;
+              ptx::bulk_g2s_multicast(ring + (size_t)slot * kStageBytes + crank * kHalf,
+                                      src + (size_t)img * kStageBytes + crank * kHalf, kHalf, &tail->b_full[slot], 0x3);
+            } else {
+              ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)img * kStageBytes, kStageBytes,
+                            &tail->b_full[slot]);
+            }
             if (++slot == num_stages) { slot = 0; phase ^= 1u; }
           }
         }
@@ -667,6 +696,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     __syncwarp();
   }
   __syncthreads();
+  if (CLUSTER) ptx::cluster_sync_all();  // no CTA of the pair exits while the other may still signal its barriers
   if (warp == kTcEpiWarps) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::kTmemCols);
@@ -869,10 +899,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_backward_kernel(cnf_dims d, 
           const uint8_t* src = wsrc + (size_t)l * C::kStagesPerLayer * kStageBytes;
           for (int s = 0; s < C::kStagesPerLayer; ++s) {
             int img = s;  // block pipeline: quadrant order, see the forward kernel's producer
-            if (C::kBlockPipe) {
-              constexpr int NB = C::kNBlocks, kSPQ = 2 * C::kParts;
-              const int q = s / kSPQ, r = s % kSPQ;
-              const int k = q / NB, n = q % NB, ks = 2 * k + r / C::kParts, part = r % C::kParts;
+            if (C::kBlockPipe) {  // consumed episode by episode: K slab -> row block n -> part (tc_issue_block)
+              constexpr int NB = C::kNBlocks;
+              const int e = s / C::kParts, part = s % C::kParts;
+              const int ks = e / NB, n = e % NB;
               img = (ks * C::kParts + part) * NB + n;
             }
             ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);

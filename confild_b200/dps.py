@@ -38,9 +38,28 @@ def _mask_kind(mask: torch.Tensor, T: int, P: int, cout: int) -> Tuple[torch.Ten
     return m.expand(torch.broadcast_shapes(tuple(m.shape), (T, P, cout))).reshape(T, P, cout).contiguous(), 3
 
 
+#: per-point masks seen so far -> indices of their non-zero rows (a DPS loop passes the same mask tensor every step, so
+#: the one host synchronisation that `nonzero` costs is paid once); keyed on (data_ptr, version, numel, device)
+_ROW_CACHE: dict = {}
+#: skip the backward stash for masked-out rows when at most this fraction of the points carries a non-zero weight
+ZERO_ROW_SKIP_MAX_FRACTION = 0.5
+
+
+def _kept_rows(mask1d: torch.Tensor) -> torch.Tensor:
+    key = (mask1d.data_ptr(), mask1d._version, mask1d.numel(), str(mask1d.device))
+    idx = _ROW_CACHE.get(key)
+    if idx is None:
+        if len(_ROW_CACHE) > 64:
+            _ROW_CACHE.clear()
+        idx = torch.nonzero(mask1d != 0, as_tuple=False).reshape(-1)
+        _ROW_CACHE[key] = idx
+    return idx
+
+
 class _MeasurementNormFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, lat2d, coords_c, frame_stride, module, y_meas, mask, mask_kind, ya, yb, want_grad, want_field):
+    def forward(ctx, lat2d, coords_c, frame_stride, module, y_meas, mask, mask_kind, ya, yb, want_grad, want_field,
+                zero_row_skip=True):
         lib = _native.load()
         d = module._cdims()
         cin, L, H, nl, cout = module._dims_tuple
@@ -54,8 +73,18 @@ class _MeasurementNormFunction(torch.autograd.Function):
         gy = torch.empty((T, P, cout), dtype=torch.float32, device=dev)
         partials = torch.empty(_native.LOSS_PARTIALS, dtype=torch.float32, device=dev)
         norm = torch.empty(2, dtype=torch.float32, device=dev)
+        # Rows whose per-point weight is zero have an identically zero seed: with a sparse per-point mask the dense pass
+        # below runs WITHOUT the backward stash (every point is still decoded and enters the norm) and only the kept
+        # rows are decoded a second time with the stash for the backward -- the stash traffic (2.8 KB / 12 KB per
+        # point-frame at case1 / case4) shrinks by P / #kept while the gradient stays exact.
+        kept = None
+        if (want_grad and zero_row_skip and mask is not None and mask_kind == 1 and frame_stride == 0
+                and prec != _native.PREC_FP32):
+            idx = _kept_rows(mask)
+            if 0 < idx.numel() <= ZERO_ROW_SKIP_MAX_FRACTION * P:
+                kept = idx
         stash, stash_n = None, 0
-        if want_grad:
+        if want_grad and kept is None:
             stash_n = _native.stash_bytes(d, prec, T, P)
             stash = torch.empty(stash_n, dtype=torch.uint8, device=dev)
         loss = _native.CnfSensorLoss()
@@ -78,8 +107,19 @@ class _MeasurementNormFunction(torch.autograd.Function):
             if want_grad:  # the gradient is a by-product of the step: run the chain backward now and free the stash
                 gshift = torch.empty((T, (nl + 1) * H), dtype=torch.float32, device=dev)
                 glat = torch.empty((T, L), dtype=torch.float32, device=dev)
-                _native.check(lib.cnf_backward(d, packed.data_ptr(), prec, gy.data_ptr(), stash.data_ptr(), stash_n,
-                                               gshift.data_ptr(), T, P, stream), "cnf_backward")
+                Pb, gy_b = P, gy
+                if kept is not None:  # second, stash-writing decode of the kept rows only (same FiLM shifts)
+                    Pb = int(kept.numel())
+                    coords_k = coords_c.index_select(0, kept).contiguous()
+                    gy_b = gy.index_select(1, kept).contiguous()
+                    stash_n = _native.stash_bytes(d, prec, T, Pb)
+                    stash = torch.empty(stash_n, dtype=torch.uint8, device=dev)
+                    scratch = torch.empty((T, Pb, cout), dtype=torch.float32, device=dev)
+                    _native.check(lib.cnf_forward(d, packed.data_ptr(), prec, coords_k.data_ptr(), 0, shift.data_ptr(),
+                                                  scratch.data_ptr(), T, Pb, stash.data_ptr(), stash_n, stream),
+                                  "cnf_forward")
+                _native.check(lib.cnf_backward(d, packed.data_ptr(), prec, gy_b.data_ptr(), stash.data_ptr(), stash_n,
+                                               gshift.data_ptr(), T, Pb, stream), "cnf_backward")
                 _native.check(lib.cnf_film_shift_backward_scaled(d, packed.data_ptr(), gshift.data_ptr(), T,
                                                                  norm[1:].data_ptr(), glat.data_ptr(), stream),
                               "cnf_film_shift_backward_scaled")
@@ -94,12 +134,12 @@ class _MeasurementNormFunction(torch.autograd.Function):
     def backward(ctx, gnorm, _gfield):
         if ctx.glat is None:
             raise RuntimeError("measurement_norm was evaluated without gradient tracking of the latents")
-        return ctx.glat * gnorm, None, None, None, None, None, None, None, None, None, None
+        return ctx.glat * gnorm, None, None, None, None, None, None, None, None, None, None, None
 
 
 def measurement_norm(model: SIRENAutodecoder_film, coords: torch.Tensor, latents: torch.Tensor,
                      measurement: torch.Tensor, mask: Optional[torch.Tensor] = None, y_normalizer=None,
-                     mask_measurement: bool = False, return_field: bool = False):
+                     mask_measurement: bool = False, return_field: bool = False, zero_row_skip: bool = True):
     """``torch.linalg.norm(measurement - mask * y_normalizer.denormalize(model(coords, latents)))`` as one fused
     CUDA pass, differentiable with respect to ``latents``.
 
@@ -108,6 +148,8 @@ def measurement_norm(model: SIRENAutodecoder_film, coords: torch.Tensor, latents
     ``mask_measurement=True`` evaluates ``mask * (measurement - y)`` instead by masking the
     measurement first.  ``y_normalizer`` is the reference's ``Normalizer_ts`` (any of its affine methods) or ``None``.
     With ``return_field=True`` returns ``(norm, y_phys)`` where ``y_phys`` is the decoded (denormalised, unmasked) field.
+    ``zero_row_skip`` (default on): with a sparse per-point mask the backward only visits the rows whose weight is
+    non-zero (their seed is identically zero otherwise); every point is still decoded and enters the norm.
     """
     dev = model._check_inputs(coords, latents)
     grad_on = model._check_grad_mode(coords)
@@ -130,7 +172,7 @@ def measurement_norm(model: SIRENAutodecoder_film, coords: torch.Tensor, latents
     y_meas = y_meas.expand(out_lead + (cout,)).reshape(T, P, cout).contiguous()
     want_grad = grad_on and lat2d.requires_grad
     norm, field = _MeasurementNormFunction.apply(lat2d, coords_c, stride, model, y_meas, mk, kind, ya, yb, want_grad,
-                                                 return_field)
+                                                 return_field, zero_row_skip)
     if return_field:
         ya_t = torch.tensor(ya, device=dev)
         yb_t = torch.tensor(yb, device=dev)

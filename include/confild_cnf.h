@@ -68,7 +68,8 @@ const char* cnf_last_error(void);
  * environment variables of the same name, read once per process; this call overrides one at run time (tests).
  *   "CNF_TC2"        0: route H = 128 through the generic kernels (default 1)
  *   "CNF_TC_STAGES"  n: cap the depth of the shared-memory weight ring (default 0 = as deep as fits)
- *   "CNF_TC_PACKED"  0/1: force frame-aligned / packed tiles (default -1 = by shape) */
+ *   "CNF_TC_PACKED"  0/1: force frame-aligned / packed tiles (default -1 = by shape)
+ *   "CNF_TC_CLUSTER" 0: H = 256/384 forward as single CTAs instead of CTA pairs sharing the weight stream (default 1) */
 int cnf_set_debug_knob(const char* name, int value);
 
 /* 1 if the tensor-core (tcgen05) kernels exist for these dims, else 0 (CUDA-core fp32 only). */

@@ -482,7 +482,7 @@ def test_shallow_networks_forward_and_gradient(dims, prec):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"CNF_TC2": "0"}, {"CNF_TC_STAGES": "8"}, {"CNF_TC_STAGES": "6"}])
+@pytest.mark.parametrize("env", [{"CNF_TC2": "0"}, {"CNF_TC_STAGES": "8"}, {"CNF_TC_STAGES": "6"}, {"CNF_TC_CLUSTER": "0"}])
 @pytest.mark.parametrize("case", ["case1", "case2"])
 def test_debug_knobs_keep_parity(env, case, knob):
     """The debug knobs (generic kernel for H=128, shallower weight ring) select other code paths / schedules of the same
@@ -762,6 +762,10 @@ def test_sensor_rows_compaction_matches_dense_gradient():
     l1 = lat.cuda()[:, None].requires_grad_(True)
     n_dense = cb.measurement_norm(m, c[None], l1, y_meas, mask=mk, mask_measurement=True)
     (g_dense,) = torch.autograd.grad(n_dense, l1)
+    l3 = lat.cuda()[:, None].requires_grad_(True)
+    n_full = cb.measurement_norm(m, c[None], l3, y_meas, mask=mk, mask_measurement=True, zero_row_skip=False)
+    (g_full,) = torch.autograd.grad(n_full, l3)  # dense stash for every row vs the zero-row skip (default) above
+    assert float(n_full) == float(n_dense) and O.rel_l2(g_dense, g_full) <= 1e-4
     cs, idx, ys = cb.sensor_rows(c, mk, y_meas)
     assert cs.shape == (300, dims[0]) and ys.shape == (T, 300, dims[2])
     l2 = lat.cuda()[:, None].requires_grad_(True)
@@ -769,3 +773,79 @@ def test_sensor_rows_compaction_matches_dense_gradient():
     (g_comp,) = torch.autograd.grad(n_comp, l2)
     assert abs(float(n_dense) - float(n_comp)) <= 1e-5 * float(n_dense)
     assert O.rel_l2(g_comp, g_dense) <= 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,T,P,prec", [
+    ("case1", 3, 300, "f16f8"), ("case1", 3, 300, "bf16x3"), ("case1", 37, 10, "f16f8"), ("case1", 1, 1, "bf16x3"),
+    ("case2", 2, 129, "f16f8"), ("case4", 2, 130, "f16f8"), ("case4", 26, 10, "bf16x3"), ("case1", 2, 70, "fp32")])
+def test_guard_bands_around_every_device_buffer(case, T, P, prec):
+    """compute-sanitizer is closed on this pool (profiles/r02_compute_sanitizer_closed.txt), so out-of-bounds WRITES are
+    caught with our own canaries: every buffer the C ABI writes (shift, out, stash, gy, gshift, glatents) sits between
+    guard bands of a sentinel pattern, through the raw C ABI, ragged / packed / multi-block shapes; the bands must come
+    back untouched and the results must still match the oracle."""
+    import ctypes
+
+    lib = _native.load()
+    dims = O.CASE_SHAPES[case]
+    cin, L, cout, nl, H = dims
+    sd = O.init_params(*dims, seed=0)
+    coords, lat = O.synthetic_inputs(cin, L, T, P)
+    gout = torch.randn(T, P, cout, generator=torch.Generator().manual_seed(7))
+    d = _native.dims(cin, L, H, nl, cout)
+    code = _native.PRECISIONS[prec]
+    flat = torch.cat([v.reshape(-1) for v in sd.values()]).cuda()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    G = 4096  # guard bytes on either side
+
+    def guarded(nbytes):
+        buf = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return buf, buf.data_ptr() + G
+
+    def intact(buf, nbytes):
+        return bool((buf[:G] == 0xA5).all()) and bool((buf[G + nbytes:] == 0xA5).all())
+
+    def as_f32(buf, n):
+        return buf[G:G + 4 * n].view(torch.float32)
+
+    pk_n = _native.packed_bytes(d)
+    packed, packed_p = guarded(pk_n)
+    assert lib.cnf_pack_weights(d, ctypes.c_void_p(flat.data_ptr()), ctypes.c_float(30.0), ctypes.c_void_p(packed_p), pk_n, stream) == 0
+    SH = (nl + 1) * H
+    shift, shift_p = guarded(4 * T * SH)
+    out, out_p = guarded(4 * T * P * cout)
+    st_n = _native.stash_bytes(d, code, T, P)
+    stash, stash_p = guarded(st_n)
+    gshift, gshift_p = guarded(4 * T * SH)
+    glat, glat_p = guarded(4 * T * L)
+    c_d, l_d, g_d = coords.cuda(), lat.cuda(), gout.cuda()
+    vp = ctypes.c_void_p
+    assert lib.cnf_film_shift(d, vp(packed_p), vp(l_d.data_ptr()), T, vp(shift_p), stream) == 0
+    assert lib.cnf_forward(d, vp(packed_p), code, vp(c_d.data_ptr()), 0, vp(shift_p), vp(out_p), T, P, vp(stash_p), st_n, stream) == 0
+    assert lib.cnf_backward(d, vp(packed_p), code, vp(g_d.data_ptr()), vp(stash_p), st_n, vp(gshift_p), T, P, stream) == 0
+    assert lib.cnf_film_shift_backward(d, vp(packed_p), vp(gshift_p), T, vp(glat_p), stream) == 0
+    torch.cuda.synchronize()
+    for name, buf, n in (("packed", packed, pk_n), ("shift", shift, 4 * T * SH), ("out", out, 4 * T * P * cout),
+                         ("stash", stash, st_n), ("gshift", gshift, 4 * T * SH), ("glat", glat, 4 * T * L)):
+        assert intact(buf, n), f"write outside the {name} buffer"
+    y = as_f32(out, T * P * cout).reshape(T, P, cout)
+    gl = as_f32(glat, T * L).reshape(T, L)
+    assert O.rel_l2(y, O.forward(sd, coords[None], lat[:, None])) <= FWD_TOL[prec]
+    assert O.rel_l2(gl, O.grad_latents_from_gout(sd, coords[None], lat[:, None], gout).reshape(T, L)) <= BWD_TOL[prec]
+
+
+@pytest.mark.gpu
+def test_default_precision_is_the_auto_policy():
+    dims = O.CASE_SHAPES["case1"]
+    sd = O.init_params(*dims, seed=0)
+    m = cb.SIRENAutodecoder_film(*dims[:2], dims[2], dims[3], dims[4])
+    m.load_state_dict(sd)
+    m = m.eval().cuda()
+    assert m.precision == "auto" and m.resolved_precision == "f16f8"
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], 4, 1000)
+    with torch.no_grad():
+        y = m(coords.cuda()[None], lat.cuda()[:, None])
+    ref = make_model(dims, sd, "f16f8")
+    with torch.no_grad():
+        assert torch.equal(y, ref(coords.cuda()[None], lat.cuda()[:, None]))
+    assert O.rel_l2(y, O.forward(sd, coords[None], lat[:, None])) <= FWD_EXPECT["f16f8"]
