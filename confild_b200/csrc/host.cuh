@@ -41,7 +41,7 @@ struct Knobs {
   int tc2 = 1;
   int stages = 0;
   int packed = -1;
-  int cluster = 1;  // CNF_TC_CLUSTER: H = 256/384 forward as CTA pairs sharing the weight stream (0 = single CTAs)
+  int cluster = 1;  // CNF_TC_CLUSTER: H = 256/384 forward as CTA pairs: 1 = multicast weight stages (default), 2 = cta_group::2 MMAs, 0 = single CTAs
 };
 const Knobs& knobs();
 int set_knob(const char* name, int value);  // tests / tuning: override a knob at run time

@@ -39,12 +39,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Spin until the phase with the given parity has completed.  A protocol bug would otherwise hang
 // the GPU until the watchdog: after 2^22 failed probes trap instead, so the launch fails.
+// Same probe with acquire semantics at CLUSTER scope: the arrivals being waited for came from another CTA of the cluster.
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+template <bool CLUSTER_SCOPE = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      printf("cnf: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
+  uint64_t t0 = 0;
+  while (!(CLUSTER_SCOPE ? mbar_try_wait_cluster(bar, parity) : mbar_try_wait(bar, parity))) {
+    if ((++spins & 0xFFu) == 0) {  // every 256 failed probes: wall-clock check (a probe may sleep in hardware)
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {  // 4 s without progress: a protocol bug, fail the launch instead of hanging
+        printf("cnf: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+      }
     }
   }
 }
@@ -94,6 +117,17 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 // Barrier over every thread of every CTA of the cluster (release / acquire): executed by ALL threads, converged.
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Address of `local` (a shared::cta address of THIS CTA) in the shared memory of CTA `rank` of the cluster.
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+// Arrive (release at cluster scope) on an mbarrier given by its shared::cluster address (own or peer CTA).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // ---------------------------------------------------------------- named barriers
@@ -166,6 +200,44 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // Same arrival delivered to the mbarrier at the same CTA-relative offset in every CTA of `cta_mask`.
 __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) forms: one instruction, issued by a thread of the leader CTA, drives the tensor cores of
+// both CTAs of a 2-CTA cluster: M = 256 = 128 rows per CTA (each CTA's own A operand and accumulator), the B operand
+// split along N (each CTA's shared memory holds N/2 of its rows).  All addresses are CTA-relative (same in both CTAs).
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {  // one full warp in EACH CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+#define CNF_DEFINE_UMMA_PAIR(name, kind, aop, atype, aconstraint)                                              \
+  __device__ __forceinline__ void name(uint32_t tmem_d, atype a, uint64_t desc_b, uint32_t idesc,             \
+                                       uint32_t accumulate) {                                                 \
+    asm volatile(                                                                                             \
+        "{\n\t.reg .pred p;\n\t"                                                                             \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                                           \
+        "tcgen05.mma.cta_group::2.kind::" kind " [%0], " aop ", %2, %3, p;\n\t}" ::"r"(tmem_d),               \
+        aconstraint(a), "l"(desc_b), "r"(idesc), "r"(accumulate)                                              \
+        : "memory");                                                                                          \
+  }
+CNF_DEFINE_UMMA_PAIR(umma_f16_ss_pair, "f16", "%1", uint64_t, "l")
+CNF_DEFINE_UMMA_PAIR(umma_f16_ts_pair, "f16", "[%1]", uint32_t, "r")
+CNF_DEFINE_UMMA_PAIR(umma_f8_ss_pair, "f8f6f4", "%1", uint64_t, "l")
+CNF_DEFINE_UMMA_PAIR(umma_f8_ts_pair, "f8f6f4", "[%1]", uint32_t, "r")
+#undef CNF_DEFINE_UMMA_PAIR
+// Completion of every cta_group::2 MMA issued so far by this thread, delivered to the mbarrier at the same CTA-relative
+// offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    smem_u32(bar)),
                "h"(cta_mask)
                : "memory");

@@ -8,7 +8,7 @@ namespace {
 
 template <int H, int PREC, bool STASH>
 int launch_tc_forward(const FwdArgs& a) {
-  static std::atomic<size_t> smem_set[4][kMaxDevices];
+  static std::atomic<size_t> smem_set[6][kMaxDevices];
   DeviceInfo di;
   if (int rc = device_info(&di)) return rc;
   const int pack_rows = use_packed(a.P);
@@ -22,13 +22,20 @@ int launch_tc_forward(const FwdArgs& a) {
   // frame-aligned tiles of the block-pipelined kernels stage the layer's FiLM shifts in shared memory
   constexpr bool kCanStage = TcCfg<H, PREC>::kBlockPipe;
   const bool stage = kCanStage && !pack_rows;
-  // CTA pairs that share every weight stage (multicast halves): worth it once there are at least two tiles per SM pair
+  // CTA pairs (2-CTA clusters) that share the weight stream: worth it once there are at least two tiles.
+  //   CNF_TC_CLUSTER = 1 (default): every stage multicast into both rings;  2: cta_group::2 MMAs, each CTA holds half of
+  //   every stage (works, but every pair MMA then costs ~230 clk: 1.9x slower end to end, kept for further work)
   constexpr bool kCanCluster = TcCfg<H, PREC>::kBlockPipe;
-  const bool cluster = kCanCluster && knobs().cluster != 0 && tiles >= 2;
-  if (cluster) {
-    auto kern = stage ? tc_forward_kernel<H, PREC, STASH, kCanStage, kCanCluster>
-                      : tc_forward_kernel<H, PREC, STASH, false, kCanCluster>;
-    if (int rc = ensure_smem(kern, plan.smem, di.device, smem_set[2 + (stage ? 1 : 0)])) return rc;
+  const int cm = (kCanCluster && tiles >= 2) ? knobs().cluster : 0;
+  if (cm == kClusterMcast || cm == kClusterPair) {
+    if (cm == kClusterPair)
+      if (int rc = make_tc_plan<H, PREC>(di, tiles, &plan, tc_slot_bytes(kClusterPair))) return rc;
+    auto kern = cm == kClusterPair
+                    ? (stage ? tc_forward_kernel<H, PREC, STASH, kCanStage, kCanCluster ? kClusterPair : 0>
+                             : tc_forward_kernel<H, PREC, STASH, false, kCanCluster ? kClusterPair : 0>)
+                    : (stage ? tc_forward_kernel<H, PREC, STASH, kCanStage, kCanCluster ? kClusterMcast : 0>
+                             : tc_forward_kernel<H, PREC, STASH, false, kCanCluster ? kClusterMcast : 0>);
+    if (int rc = ensure_smem(kern, plan.smem, di.device, smem_set[2 * cm + (stage ? 1 : 0)])) return rc;
     int64_t grid = (tiles + 1) & ~(int64_t)1;
     const int64_t cap = di.sms & ~1;
     if (grid > cap) grid = cap;

@@ -59,7 +59,6 @@ struct TcCfg {
   static constexpr bool kBlockPipe = (H == 256 || H == 384);
   static constexpr uint32_t kTmemCols = (H + kATmemCols) <= 256 ? 256u : 512u;
   static constexpr uint32_t kIdesc = ptx::make_idesc_f16(kSplit ? 1u : 0u, kTileM, kStageRows);
-  static constexpr uint32_t kIdescF8 = ptx::make_idesc_f8(ptx::kF8E5M2, ptx::kF8E4M3, kTileM, kStageRows);
   static_assert(kColsPerGroup % 16 == 0, "column groups are processed 16 columns at a time");
   static_assert(!kF8 || kBlockPipe, "f16f8 is implemented for the block-pipelined widths (H = 256, 384) here; H = 128 has tc2");
 };
@@ -77,10 +76,19 @@ struct TcSmemTail {  // lives after the A operand and the weight ring
   uint32_t tmem_base;
 };
 
+// Cluster modes of the block-pipelined forward kernel (template parameter CM):
+//   kClusterNone   single CTAs
+//   kClusterMcast  2-CTA clusters, different tiles, every weight stage fetched once per pair and MULTICAST into both rings
+//   kClusterPair   2-CTA clusters driven by cta_group::2 MMAs issued from the leader CTA: M = 256 = the two CTAs' tiles,
+//                  the weight operand split along N, so each CTA stores and reads only HALF of every weight stage --
+//                  which is what relieves the H = 384 kernel's bound, shared-memory bandwidth
+constexpr int kClusterNone = 0, kClusterMcast = 1, kClusterPair = 2;
+__host__ __device__ constexpr int tc_slot_bytes(int cm) { return cm == kClusterPair ? kStageBytes / 2 : kStageBytes; }
+
 template <int H, int PREC>
-__host__ __device__ constexpr size_t tc_smem_bytes(int num_stages) {
+__host__ __device__ constexpr size_t tc_smem_bytes(int num_stages, int slot_bytes = kStageBytes) {
   static_assert(sizeof(TcSmemTail) <= kTcTailBytes, "TcSmemTail outgrew its reserved area");
-  return 1024 /*alignment slack*/ + (size_t)TcCfg<H, PREC>::kABytes + (size_t)num_stages * kStageBytes + kTcTailBytes +
+  return 1024 /*alignment slack*/ + (size_t)TcCfg<H, PREC>::kABytes + (size_t)num_stages * slot_bytes + kTcTailBytes +
          (TcCfg<H, PREC>::kABytes >= 4 * kTileM * 16 ? 0 : 4 * kTileM * 16) + (size_t)H * 4 /* staged FiLM shifts */;
 }
 
@@ -225,33 +233,55 @@ __device__ __forceinline__ void tc_store_a16(uint8_t* a_smem, uint32_t tmem_row,
 }
 
 // Common prologue: barriers, TMEM allocation.  Returns the TMEM base.
-template <int H, int PREC, bool CLUSTER = false>
+template <int H, int PREC, int CM = kClusterNone>
 __device__ __forceinline__ uint32_t tc_setup(TcSmemTail* tail, int num_stages, int warp) {
   using C = TcCfg<H, PREC>;
   if (threadIdx.x == 0) {
+    const bool leader = CM != kClusterPair || ptx::cluster_ctarank() == 0;
     for (int s = 0; s < num_stages; ++s) {
-      ptx::mbar_init(&tail->b_full[s], 1);
-      ptx::mbar_init(&tail->b_empty[s], CLUSTER ? 2 : 1);  // cluster: released by the issuers of both CTAs
+      // pair: the leader's barrier also counts the relayed arrival of the peer's half of the stage
+      ptx::mbar_init(&tail->b_full[s], (CM == kClusterPair && leader) ? 2 : 1);
+      ptx::mbar_init(&tail->b_empty[s], CM == kClusterMcast ? 2 : 1);  // multicast: released by the issuers of both CTAs
     }
     ptx::mbar_init(&tail->a_full, kTcEpiWarps * 32);
     ptx::mbar_init(&tail->d_full, 1);
+    // pair: one (warp-aggregated) arrival per activation warp of BOTH CTAs, on the leader's barriers
+    constexpr uint32_t kEpiArrivals = CM == kClusterPair ? 2 * kTcEpiWarps : kTcEpiWarps * 32;
     for (int n = 0; n < 3; ++n) {
-      ptx::mbar_init(&tail->e_done[n], kTcEpiWarps * 32);
-      ptx::mbar_init(&tail->d_drained[n], kTcEpiWarps * 32);
+      ptx::mbar_init(&tail->e_done[n], kEpiArrivals);
+      ptx::mbar_init(&tail->d_drained[n], kEpiArrivals);
       ptx::mbar_init(&tail->d_done[n], 1);
       ptx::mbar_init(&tail->turn[n], 1);
     }
     ptx::fence_mbar_init();
   }
   if (warp == kTcEpiWarps) {
-    ptx::tmem_alloc(&tail->tmem_base, C::kTmemCols);
-    ptx::tmem_relinquish();
+    if (CM == kClusterPair) {
+      ptx::tmem_alloc_pair(&tail->tmem_base, C::kTmemCols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(&tail->tmem_base, C::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CLUSTER) ptx::cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
+  if (CM != kClusterNone) ptx::cluster_sync_all();  // the peer's barriers exist before anything is signalled to them
   ptx::tc_fence_after();
   return tail->tmem_base;
+}
+
+// Activation-warp arrival on an issuer-facing barrier (e_done / d_drained).  Single CTA / multicast: every thread
+// arrives on its own CTA's barrier.  Pair: the MMAs of both CTAs are issued by the leader, so each warp (after its
+// threads' own fences) sends ONE arrival to the LEADER's barrier, release at cluster scope.
+template <int CM>
+__device__ __forceinline__ void tc_epi_arrive(uint64_t* bar) {
+  if (CM != kClusterPair) {
+    ptx::mbar_arrive(bar);
+  } else {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(bar), 0));
+  }
 }
 
 // Activation warps wait for the layer's accumulator: one warp polls the mbarrier, the others sleep on a named barrier.
@@ -267,7 +297,7 @@ __device__ __forceinline__ void tc_wait_d_full(TcSmemTail* tail, int warp, uint3
 // 16-column groups.  Both groups are loaded at once; for n >= 1 the thread then arrives on d_drained[n] (the issuer may
 // overwrite the block with the next layer's Q'(n,0)); sines, bf16 split, store into K part n of the next A operand,
 // arrive on e_done[n].  LAST: output head instead of the stores, no arrivals.
-template <int H, int PREC, bool LAST, bool STASH>
+template <int H, int PREC, bool LAST, bool STASH, int CM = kClusterNone>
 __device__ __forceinline__ void tc_block_epilogue(int n, uint8_t* a_smem, uint32_t tmem_row, int row, int cg,
                                                   const float* __restrict__ shl, const float* __restrict__ w_out,
                                                   int cout, float (&y)[4], __half* stash_l, TcSmemTail* tail,
@@ -281,7 +311,7 @@ __device__ __forceinline__ void tc_block_epilogue(int n, uint8_t* a_smem, uint32
   ptx::tmem_wait_ld();
   if (!LAST && n > 0) {
     ptx::tc_fence_before();
-    ptx::mbar_arrive(&tail->d_drained[n]);
+    tc_epi_arrive<CM>(&tail->d_drained[n]);
   }
   tc_sines16<STASH, C::kF8>(v0, shl + c0, h0, STASH ? stash_l + (size_t)c0 * kTileM : nullptr, inv);
   tc_sines16<STASH, C::kF8>(v1, shl + c0 + 16, h1, STASH ? stash_l + (size_t)(c0 + 16) * kTileM : nullptr, inv);
@@ -291,7 +321,7 @@ __device__ __forceinline__ void tc_block_epilogue(int n, uint8_t* a_smem, uint32
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
     if (C::kABytes > 0) ptx::fence_proxy_async_smem();
-    ptx::mbar_arrive(&tail->e_done[n]);
+    tc_epi_arrive<CM>(&tail->e_done[n]);
   } else {
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
@@ -320,14 +350,18 @@ __device__ __forceinline__ void tc_block_epilogue(int n, uint8_t* a_smem, uint32
 // them).  All quadrants of block n come from this warp, so its commit after Q(n, NB-1) covers the whole block; E_n
 // additionally relies on the tensor pipe completing MMAs in issue order (the quadrants of other blocks that read K part
 // n were issued earlier).  `stage` counts the weight stages consumed so far by ALL warps (ring position).
-template <int H, int PREC, bool CLUSTER = false>
+template <int H, int PREC, int CM = kClusterNone>
 __device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t ring_addr, uint32_t tmem_d,
                                                TcSmemTail* tail, int num_stages, int& slot, uint32_t& phase,
                                                uint32_t& e_phase, uint32_t& turn_phase) {
   using C = TcCfg<H, PREC>;
   constexpr int NB = C::kNBlocks;
   constexpr int kP = C::kParts;  // weight stages of one issue episode: (hi, lo) / (fp16, fp8) / fp16 of one K slab, row block n
-  constexpr uint32_t kIdesc = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kTileM, 128);
+  constexpr bool PAIR = (CM == kClusterPair);
+  constexpr uint32_t kM = PAIR ? 2 * kTileM : kTileM;  // pair: one instruction covers the tiles of both CTAs
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kM, 128);
+  constexpr uint32_t kIdescF8 = ptx::make_idesc_f8(ptx::kF8E5M2, ptx::kF8E4M3, kM, 128);
+  constexpr int kSlot = tc_slot_bytes(CM);
   // One issue EPISODE = accumulator block n x ONE K slab: all its weight stages are awaited first, then all its MMAs
   // (12 bf16x3 / 8 f16f8 / 4 fp16) leave in a single elected-lane block with the stage releases interleaved, and the
   // token moves on.  Episodes go round-robin over the issuer warps (block 0, 1, .., NB-1 of slab 0, then slab 1, ..), so
@@ -343,14 +377,14 @@ __device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t 
 #pragma unroll 1
   for (int ks = 0; ks < C::kSlabs; ++ks) {
     // operands: K part ks/2 of A written; block n drained before its first episode overwrites it; the slab's stages landed
-    if ((ks & 1) == 0) ptx::mbar_wait(&tail->e_done[ks >> 1], e_phase);
-    if (ks == 0 && n > 0) ptx::mbar_wait(&tail->d_drained[n], e_phase);
+    if ((ks & 1) == 0) ptx::mbar_wait<PAIR>(&tail->e_done[ks >> 1], e_phase);
+    if (ks == 0 && n > 0) ptx::mbar_wait<PAIR>(&tail->d_drained[n], e_phase);
     {
       int sl = slot;
       uint32_t ph = phase;
 #pragma unroll
       for (int part = 0; part < kP; ++part) {
-        ptx::mbar_wait(&tail->b_full[sl], ph);
+        ptx::mbar_wait<PAIR>(&tail->b_full[sl], ph);
         if (++sl >= num_stages) { sl = 0; ph ^= 1u; }
       }
     }
@@ -366,26 +400,45 @@ __device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t 
       int sl = slot;
 #pragma unroll
       for (int part = 0; part < kP; ++part) {
-        const uint64_t b = ptx::make_desc_k_sw128(ring_addr + sl * kStageBytes);
+        const uint64_t b = ptx::make_desc_k_sw128(ring_addr + sl * kSlot);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint32_t first = (part == 0) ? (uint32_t)((ks | kk) != 0) : 1u;
           if (C::kF8 && part == 1) {  // fp8 stage: K = 32 per MMA; e5m2(a_lo) x e4m3(S w), then e5m2(a) x e4m3(S w_lo)
-            if (a_in_tmem) ptx::umma_f8_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, C::kIdescF8, 1u);
-            else ptx::umma_f8_ss(dcol, a_lo + 2 * kk, b + 2 * kk, C::kIdescF8, 1u);
+            if (a_in_tmem) {
+              if (PAIR) ptx::umma_f8_ts_pair(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdescF8, 1u);
+              else ptx::umma_f8_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdescF8, 1u);
+            } else {
+              if (PAIR) ptx::umma_f8_ss_pair(dcol, a_lo + 2 * kk, b + 2 * kk, kIdescF8, 1u);
+              else ptx::umma_f8_ss(dcol, a_lo + 2 * kk, b + 2 * kk, kIdescF8, 1u);
+            }
           } else if (a_in_tmem) {
-            ptx::umma_f16_ts(dcol, at_hi + kk * 8, b + 2 * kk, kIdesc, first);
-            if (C::kSplit && part == 0) ptx::umma_f16_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdesc, 1u);
+            if (PAIR) {
+              ptx::umma_f16_ts_pair(dcol, at_hi + kk * 8, b + 2 * kk, kIdesc, first);
+              if (C::kSplit && part == 0) ptx::umma_f16_ts_pair(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdesc, 1u);
+            } else {
+              ptx::umma_f16_ts(dcol, at_hi + kk * 8, b + 2 * kk, kIdesc, first);
+              if (C::kSplit && part == 0) ptx::umma_f16_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdesc, 1u);
+            }
           } else {
-            ptx::umma_f16_ss(dcol, a_hi + 2 * kk, b + 2 * kk, kIdesc, first);
-            if (C::kSplit && part == 0) ptx::umma_f16_ss(dcol, a_lo + 2 * kk, b + 2 * kk, kIdesc, 1u);
+            if (PAIR) {
+              ptx::umma_f16_ss_pair(dcol, a_hi + 2 * kk, b + 2 * kk, kIdesc, first);
+              if (C::kSplit && part == 0) ptx::umma_f16_ss_pair(dcol, a_lo + 2 * kk, b + 2 * kk, kIdesc, 1u);
+            } else {
+              ptx::umma_f16_ss(dcol, a_hi + 2 * kk, b + 2 * kk, kIdesc, first);
+              if (C::kSplit && part == 0) ptx::umma_f16_ss(dcol, a_lo + 2 * kk, b + 2 * kk, kIdesc, 1u);
+            }
           }
         }
-        if (CLUSTER) ptx::umma_commit_multicast(&tail->b_empty[sl], 0x3);  // the stage sits in both CTAs of the pair
+        if (PAIR) ptx::umma_commit_pair(&tail->b_empty[sl], 0x3);             // both CTAs' halves of the stage
+        else if (CM == kClusterMcast) ptx::umma_commit_multicast(&tail->b_empty[sl], 0x3);  // the stage sits in both CTAs
         else ptx::umma_commit(&tail->b_empty[sl]);
         if (++sl >= num_stages) sl = 0;
       }
-      if (ks == C::kSlabs - 1) ptx::umma_commit(&tail->d_done[n]);
+      if (ks == C::kSlabs - 1) {
+        if (PAIR) ptx::umma_commit_pair(&tail->d_done[n], 0x3);  // the block is complete in both CTAs
+        else ptx::umma_commit(&tail->d_done[n]);
+      }
       ptx::mbar_arrive(&tail->turn[n + 1 == NB ? 0 : n + 1]);
     }
     __syncwarp();
@@ -403,7 +456,7 @@ __device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t 
 // stages: each CTA fetches half of every 16 KiB stage and multicasts it into both CTAs' rings, so a weight byte is read
 // from L2 once per CTA PAIR (the H = 384 kernel is bound by that stream: ~30 B/clk/SM whatever the precision).  A ring
 // slot is refilled only after the issuers of BOTH CTAs have released it (b_empty counts two multicast commits).
-template <int H, int PREC, bool STASH, bool STAGE = false, bool CLUSTER = false>
+template <int H, int PREC, bool STASH, bool STAGE = false, int CM = kClusterNone>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, const uint8_t* __restrict__ packed,
                                                                    const float* __restrict__ coords,
                                                                    int64_t coord_frame_stride,
@@ -416,7 +469,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_smem = smem;
   uint8_t* ring = smem + C::kABytes;
-  TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(ring + (size_t)num_stages * kStageBytes);
+  constexpr bool CLUSTER = (CM != kClusterNone);
+  constexpr bool PAIR = (CM == kClusterPair);
+  constexpr int kSlot = tc_slot_bytes(CM);  // bytes of one ring slot: a whole stage, or this CTA's half of it (pair)
+  TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(ring + (size_t)num_stages * kSlot);
 
   const PackedLayout lay = make_layout(d);
   const int nl = d.nl, cin = d.cin, cout = d.cout;
@@ -425,7 +481,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
   const int64_t tiles = tc_num_tiles(T, P, pack_rows);
   const int64_t SH = (int64_t)(nl + 1) * H;
   static_assert(!CLUSTER || C::kBlockPipe, "the CTA-pair weight multicast is implemented for the block pipeline");
-  const uint32_t tmem_base = tc_setup<H, PREC, CLUSTER>(tail, num_stages, warp);
+  const uint32_t tmem_base = tc_setup<H, PREC, CM>(tail, num_stages, warp);
   // Tile walk.  Cluster: the pair (even, odd CTA) takes tiles (base, base + 1); both CTAs run the same number of
   // iterations (they share every weight stage), an odd tile count leaves the odd CTA re-decoding the last tile with
   // its results discarded (live == false).
@@ -474,7 +530,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
       // ---- layer 0: K = cin on CUDA cores, always range-reduced (|arg| reaches tens of radians)
       if (C::kBlockPipe) {  // no accumulator to drain before the tile's first MMAs (phases must still advance)
         ptx::tc_fence_before();
-        for (int n = 1; n < C::kNBlocks; ++n) ptx::mbar_arrive(&tail->d_drained[n]);
+        for (int n = 1; n < C::kNBlocks; ++n) tc_epi_arrive<CM>(&tail->d_drained[n]);
       }
 #pragma unroll 1
       for (int c = 0; c < C::kColsPerGroup / 16; ++c) {
@@ -498,7 +554,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
           ptx::tmem_wait_st();
           ptx::tc_fence_before();
           ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&tail->e_done[c / 2]);
+          tc_epi_arrive<CM>(&tail->e_done[c / 2]);
         }
       }
       if (!C::kBlockPipe) {
@@ -531,14 +587,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
             // two call sites per variant so that each sees a pointer of known address space (ld.shared vs ld.global)
             if constexpr (STAGE) {
               if (!last)
-                tc_block_epilogue<H, PREC, false, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail, inv);
+                tc_block_epilogue<H, PREC, false, STASH, CM>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail, inv);
               else
-                tc_block_epilogue<H, PREC, true, STASH>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail, inv);
+                tc_block_epilogue<H, PREC, true, STASH, CM>(n, a_smem, tmem_row, row, cg, shift_s, w_out, cout, y, stl, tail, inv);
             } else {
               if (!last)
-                tc_block_epilogue<H, PREC, false, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail, inv);
+                tc_block_epilogue<H, PREC, false, STASH, CM>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail, inv);
               else
-                tc_block_epilogue<H, PREC, true, STASH>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail, inv);
+                tc_block_epilogue<H, PREC, true, STASH, CM>(n, a_smem, tmem_row, row, cg, shl, w_out, cout, y, stl, tail, inv);
             }
             if (tracer) CNF_TRACE_EVENT(trole, 600 + 10 * l + n);  // epilogue of block n done
           }
@@ -637,12 +693,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     uint32_t b_phase = 0, a_phase = 0;
     CNF_TRACE_DECL;
     if constexpr (C::kBlockPipe) {
-      if (which < C::kNBlocks) {  // issuer warp n owns accumulator block n (see tc_issue_block)
+      if (PAIR && crank != 0) {
+        // peer CTA of a pair: the leader issues the MMAs of both tiles.  One warp here relays "my half of stage s has
+        // landed" to the leader's b_full[s] (a bulk copy can only signal a barrier of the CTA it writes to).
+        if (which == 0) {
+          int rs = 0;
+          uint32_t rph = 0;
+          for (int64_t tbase = tile_first; tbase < tile_end; tbase += gridDim.x) {
+            for (int i = 0; i < nl * C::kStagesPerLayer; ++i) {
+              ptx::mbar_wait(&tail->b_full[rs], rph);
+              if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&tail->b_full[rs]), 0));
+              __syncwarp();
+              if (++rs == num_stages) { rs = 0; rph ^= 1u; }
+            }
+          }
+        }
+      } else if (which < C::kNBlocks) {  // issuer warp n owns accumulator block n (see tc_issue_block)
         uint32_t turn_phase = which == 0 ? 1u : 0u;  // block 0 first (a fresh barrier passes a parity-1 wait)
         for (int64_t tbase = tile_first; tbase < tile_end; tbase += gridDim.x) {
           for (int l = 1; l <= nl; ++l) {
-            tc_issue_block<H, PREC, CLUSTER>(which, a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase,
-                                             turn_phase);
+            tc_issue_block<H, PREC, CM>(which, a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase,
+                                        turn_phase);
             if (lane == 0) CNF_TRACE_EVENT(2 + which, 3000 + l);  // block `which` of layer l issued and committed
           }
         }
@@ -679,12 +750,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
               img = (ks * C::kParts + part) * NB + n;
             }
             ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kStageBytes);
-            if (CLUSTER) {  // this CTA's half of the stage, delivered to both CTAs (the peer sends the other half)
-              constexpr uint32_t kHalf = kStageBytes / 2;
+            constexpr uint32_t kHalf = kStageBytes / 2;
+            if (PAIR) {  // this CTA's N-half of the stage (64 weight rows) into its own ring; the MMA reads both CTAs' halves
+              ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kHalf);
+              ptx::bulk_g2s(ring + (size_t)slot * kHalf, src + (size_t)img * kStageBytes + crank * kHalf, kHalf,
+                            &tail->b_full[slot]);
+            } else if (CLUSTER) {  // this CTA's half of the stage, delivered to both CTAs (the peer sends the other half)
+              ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kStageBytes);
               ptx::bulk_g2s_multicast(ring + (size_t)slot * kStageBytes + crank * kHalf,
                                       src + (size_t)img * kStageBytes + crank * kHalf, kHalf, &tail->b_full[slot], 0x3);
             } else {
+              ptx::mbar_arrive_expect_tx(&tail->b_full[slot], kStageBytes);
               ptx::bulk_g2s(ring + (size_t)slot * kStageBytes, src + (size_t)img * kStageBytes, kStageBytes,
                             &tail->b_full[slot]);
             }
@@ -699,7 +775,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
   if (CLUSTER) ptx::cluster_sync_all();  // no CTA of the pair exits while the other may still signal its barriers
   if (warp == kTcEpiWarps) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 

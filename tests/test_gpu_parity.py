@@ -482,7 +482,7 @@ def test_shallow_networks_forward_and_gradient(dims, prec):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"CNF_TC2": "0"}, {"CNF_TC_STAGES": "8"}, {"CNF_TC_STAGES": "6"}, {"CNF_TC_CLUSTER": "0"}])
+@pytest.mark.parametrize("env", [{"CNF_TC2": "0"}, {"CNF_TC_STAGES": "8"}, {"CNF_TC_STAGES": "6"}, {"CNF_TC_CLUSTER": "0"}, {"CNF_TC_CLUSTER": "2"}])
 @pytest.mark.parametrize("case", ["case1", "case2"])
 def test_debug_knobs_keep_parity(env, case, knob):
     """The debug knobs (generic kernel for H=128, shallower weight ring) select other code paths / schedules of the same
