@@ -483,6 +483,71 @@ def measure_config3(cb, dev, world, rank, args):
     return res
 
 
+def measure_config5(cb, model, dev, world, rank, args):
+    """BASELINE.json configs[4]: full unconditional generation -- 1,000-step DDPM sampling of the latent image with the
+    case1 U-Net (training_recipes/case1.yml: 128 x 128, 128 channels, 2 res blocks, attention at 32/16/8; random-init
+    weights: no checkpoint offline) followed by the CNF decode of every generated frame.  16 samples over 8 GPUs in the
+    reference recipe = 2 samples per rank, kept per rank at every N (weak scaling).  Sampler and decode are timed
+    separately (the decode is the graded part); the sampler's per-step time is also given for plain fp32 eager PyTorch
+    (what the reference runs), measured over a few steps."""
+    import torch.distributed as dist
+
+    per_rank, Tl, Ll = 2, 128, 128
+    steps = args.config5_steps
+    torch.manual_seed(1234 + rank)
+    unet = cb.LatentUNet(image_size=128, num_channels=128, num_res_blocks=2, num_heads=4, num_head_channels=64,
+                         attention_resolutions="32,16,8").eval().to(dev)
+    coords_h, _ = synthetic_inputs(DIMS[0], DIMS[1], 1, POINTS)
+    xn = Affine11(torch.tensor([1.0, 1.0]), torch.tensor([-1.0, -1.0]))
+    yn = Affine11(torch.tensor([2.0, 1.5, 1.0]), torch.tensor([-2.0, -1.5, -1.0]))
+    hi, lo = torch.full((Ll,), 0.3), torch.full((Ll,), -0.3)
+    out_h = torch.empty((per_rank * Tl, POINTS, DIMS[2]), dtype=torch.float32, pin_memory=True)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    cb.sample_latents(unet, (per_rank, 1, Tl, Ll), steps=3, device=dev)  # warm-up (autotune, graph capture path)
+    sync()
+    t0 = time.perf_counter()
+    z = cb.sample_latents(unet, (per_rank, 1, Tl, Ll), steps=steps, device=dev)
+    sync()
+    t_sample = time.perf_counter() - t0
+    lat = ((z[:, 0] + 1) * (hi.to(dev) - lo.to(dev)) / 2 + lo.to(dev)).reshape(per_rank * Tl, Ll)
+    cb.decoder(coords_h, lat, model, xn, yn, 16, dev, out=out_h)
+    sync()
+    t0 = time.perf_counter()
+    cb.decoder(coords_h, lat, model, xn, yn, 16, dev, out=out_h)
+    sync()
+    t_decode = time.perf_counter() - t0
+    # the reference's way of running the sampler: fp32 eager, one Python-driven step at a time
+    n_e = 10
+    cb.sample_latents(unet, (per_rank, 1, Tl, Ll), steps=2, device=dev, autocast_dtype=None, use_cuda_graph=False)
+    sync()
+    t0 = time.perf_counter()
+    cb.sample_latents(unet, (per_rank, 1, Tl, Ll), steps=n_e, device=dev, autocast_dtype=None, use_cuda_graph=False)
+    sync()
+    t_eager_step = (time.perf_counter() - t0) / n_e
+    tt = torch.tensor([t_sample, t_decode, t_eager_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_sample, t_decode, t_eager_step = (float(v) for v in tt)
+    frames = world * per_rank * Tl
+    del unet
+    torch.cuda.empty_cache()
+    return {"workload": f"BASELINE.json configs[4]: {world * per_rank} samples ({per_rank} per GPU) x {steps}-step DDPM of a "
+                        f"(1,{Tl},{Ll}) latent image with the case1 U-Net (92 M parameters, random init), then CNF decode of "
+                        f"{frames} frames x {POINTS} points to pinned host memory",
+            "sampler_s": t_sample, "sampler_ms_per_step": t_sample / steps * 1e3,
+            "sampler": "bf16 autocast, fused attention, channels-last, one step captured in a CUDA graph",
+            "sampler_eager_fp32_ms_per_step": t_eager_step * 1e3,
+            "sampler_speedup_vs_eager_fp32": t_eager_step / (t_sample / steps),
+            "decode_s": t_decode, "decode_point_frames_per_s": frames * POINTS / t_decode, "unit": UNIT,
+            "total_s": t_sample + t_decode, "samples": world * per_rank, "steps": steps}
+
+
 def main_ours(args):
     import torch.distributed as dist
 
@@ -616,6 +681,8 @@ def main_ours(args):
         del coords, lat, flush
         torch.cuda.empty_cache()
         extra["config3_case4_sharded"] = measure_config3(cb, dev, world, rank, args)
+        if args.config5_steps > 0:
+            extra["config5_generation"] = measure_config5(cb, model, dev, world, rank, args)
 
     if rank == 0:
         peaks, peak_src = load_peaks()
@@ -670,6 +737,7 @@ def main():
     ap.add_argument("--points", type=int, default=POINTS)
     ap.add_argument("--config3-frames", type=int, default=CONFIG3_FRAMES, help="total frames of extra.config3_case4_sharded")
     ap.add_argument("--config3-steps", type=int, default=3)
+    ap.add_argument("--config5-steps", type=int, default=1000, help="DDPM steps of extra.config5_generation (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (other precisions, DPS, case4, config 3)")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N>1: how the decoded field is all-gathered")

@@ -1,0 +1,157 @@
+"""f4: the state-dict-compatible inference U-Net and the DDPM sampler against fixtures made from the
+live reference (tests/golden/make_unet_golden.py), on CPU; the bf16 / SDPA / CUDA-graph fast path on the GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import confild_b200 as cb
+from confild_b200.latent_sampler import DDPMSchedule, LatentUNet, ddpm_step, sample_latents
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LAYOUTS = json.load(open(os.path.join(GOLD, "unet_layouts.json")))
+
+
+def seeded_weights(sd):
+    g = torch.Generator().manual_seed(1)
+    return {k: torch.randn(v.shape, generator=g) * 0.05 for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("name", ["tiny", "case1", "case4"])
+def test_state_dict_layout_matches_reference(name):
+    """Keys, order and shapes equal the reference's create_model(...) for the recipe arguments: ema_*.pt loads as is."""
+    spec = LAYOUTS[name]
+    with torch.device("meta"):
+        m = LatentUNet(**spec["config"])
+    got = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+    assert got == spec["state_dict"]
+
+
+def test_same_seed_gives_reference_initial_weights():
+    g = np.load(os.path.join(GOLD, "unet_tiny.npz"))
+    torch.manual_seed(0)
+    m = LatentUNet(**LAYOUTS["tiny"]["config"])
+    total = float(sum(v.double().abs().sum() for v in m.state_dict().values()))
+    assert abs(total - float(g["init_abs_sum_seed0"])) <= 1e-9 * total
+
+
+def test_forward_and_sampler_step_match_reference_fixture():
+    g = np.load(os.path.join(GOLD, "unet_tiny.npz"))
+    torch.set_num_threads(1)
+    m = LatentUNet(**LAYOUTS["tiny"]["config"]).eval()
+    m.load_state_dict(seeded_weights(m.state_dict()))
+    x, t = torch.from_numpy(g["x"]), torch.from_numpy(g["t"])
+    with torch.no_grad():
+        y = m(x, t)
+    want = torch.from_numpy(g["y"])
+    assert float((y - want).norm() / want.norm()) <= 1e-5
+    tab = DDPMSchedule(1000, "cosine").table("cpu")
+    noise = torch.from_numpy(g["noise_seed5"])
+    for ti in (999, 500, 1, 0):
+        tt = torch.tensor([ti, ti])
+        with torch.no_grad():
+            out = ddpm_step(m(x, tt), x, tab[ti], noise)
+        ref = torch.from_numpy(g[f"p_sample_{ti}"])
+        assert float((out - ref).norm() / ref.norm()) <= 1e-5, ti
+
+
+def test_schedule_tables_match_reference():
+    g = np.load(os.path.join(GOLD, "unet_tiny.npz"))
+    s = DDPMSchedule(1000, "cosine")
+    np.testing.assert_allclose(s.betas, g["betas"], rtol=1e-12)
+    np.testing.assert_allclose(s.sqrt_recip_acp, g["sqrt_recip_alphas_cumprod"], rtol=1e-12)
+    np.testing.assert_allclose(s.post_coef1, g["posterior_mean_coef1"], rtol=1e-12)
+    np.testing.assert_allclose(s.post_coef2, g["posterior_mean_coef2"], rtol=1e-12)
+    assert DDPMSchedule(50, "linear").betas.shape == (50,)
+
+
+def test_live_reference_when_present():
+    import sys
+
+    ref_root = "/root/reference/UnconditionalDiffusionTraining_and_Generation"
+    if not os.path.isdir(ref_root):
+        pytest.skip("reference checkout not present (GPU box)")
+    sys.path.insert(0, ref_root)
+    from src.script_util import create_model  # type: ignore
+
+    cfg = LAYOUTS["tiny"]["config"]
+    torch.manual_seed(0)
+    ref = create_model(**cfg).eval()
+    torch.manual_seed(0)
+    mine = LatentUNet(**cfg).eval()
+    for (k1, v1), (k2, v2) in zip(ref.state_dict().items(), mine.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2), k1
+    sd = seeded_weights(ref.state_dict())
+    ref.load_state_dict(sd)
+    mine.load_state_dict(sd)
+    x = torch.randn(1, 1, 24, 16, generator=torch.Generator().manual_seed(3))
+    t = torch.tensor([123])
+    with torch.no_grad():
+        assert float((ref(x, t) - mine(x, t)).norm()) <= 1e-5 * float(ref(x, t).norm())
+
+
+def test_eager_sampler_runs_on_cpu_and_is_reproducible():
+    m = LatentUNet(**LAYOUTS["tiny"]["config"]).eval()
+    m.load_state_dict(seeded_weights(m.state_dict()))
+    a = sample_latents(m, (1, 1, 8, 8), steps=3, device="cpu", generator=torch.Generator().manual_seed(4))
+    b = sample_latents(m, (1, 1, 8, 8), steps=3, device="cpu", generator=torch.Generator().manual_seed(4))
+    assert a.shape == (1, 1, 8, 8) and torch.equal(a, b) and torch.isfinite(a).all()
+
+
+@pytest.mark.gpu
+def test_fast_path_matches_fp32_eager_and_graph_sampler_runs():
+    m = LatentUNet(**LAYOUTS["tiny"]["config"]).eval()
+    m.load_state_dict(seeded_weights(m.state_dict()))
+    m = m.cuda()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(4, 1, 32, 32, device="cuda", generator=g)
+    t = torch.tensor([5, 300, 700, 999], device="cuda")
+    with torch.no_grad():
+        want = m(x, t)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            got = m(x.contiguous(memory_format=torch.channels_last), t).float()
+    err = float((got - want).norm() / want.norm())
+    print(f"bf16 autocast + SDPA vs fp32 eager: rel_l2 = {err:.3e}")
+    assert err <= 5e-2
+    z = sample_latents(m, (2, 1, 32, 32), steps=6, device="cuda")  # CUDA-graph replay of one step
+    z2 = sample_latents(m, (2, 1, 32, 32), steps=6, device="cuda", use_cuda_graph=False)
+    assert z.shape == z2.shape == (2, 1, 32, 32) and torch.isfinite(z).all() and torch.isfinite(z2).all()
+    assert float(z.abs().max()) < 50 and float(z2.abs().max()) < 50
+
+
+@pytest.mark.gpu
+def test_generate_fields_end_to_end_small():
+    """Sampler -> latent de-normalisation -> batched CNF decode (scripts/inference.py:55-79 as one call)."""
+    from oracle import cnf_oracle as O
+
+    torch.manual_seed(0)
+    L, Tn, P = 32, 16, 300
+    unet = LatentUNet(image_size=64, num_channels=32, num_res_blocks=1, num_heads=4, num_head_channels=32,
+                      attention_resolutions="32,16,8").eval()
+    unet.load_state_dict(seeded_weights(unet.state_dict()))
+    unet = unet.cuda()
+    dims = (2, L, 3, 2, 128)
+    sd = O.init_params(*dims, seed=0)
+    cnf = cb.SIRENAutodecoder_film(2, L, 3, 2, 128)
+    cnf.load_state_dict(sd)
+    cnf = cnf.eval().cuda()
+    coords, _ = O.synthetic_inputs(2, L, 1, P)
+
+    class Ident:
+        method = "none"
+        params = None
+
+        def normalize(self, v):
+            return v
+
+        def denormalize(self, v):
+            return v
+
+    hi, lo = torch.full((L,), 0.3), torch.full((L,), -0.3)
+    fields, lat = cb.generate_fields(unet, cnf, coords, hi, lo, Ident(), Ident(), n_samples=2, time_length=Tn,
+                                     latent_length=L, device="cuda", steps=5)
+    assert fields.shape == (2 * Tn, P, 3) and lat.shape == (2, Tn, L) and fields.device.type == "cpu"
+    want = O.forward(sd, coords[None], lat.reshape(2 * Tn, L).cpu()[:, None])
+    assert O.rel_l2(fields, want) <= 1e-3
