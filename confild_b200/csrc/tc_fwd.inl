@@ -24,7 +24,7 @@ int launch_tc_forward(const FwdArgs& a) {
   const bool stage = kCanStage && !pack_rows;
   // CTA pairs (2-CTA clusters) that share the weight stream: worth it once there are at least two tiles.
   //   CNF_TC_CLUSTER = 1 (default): every stage multicast into both rings;  2: cta_group::2 MMAs, each CTA holds half of
-  //   every stage (works, but every pair MMA then costs ~230 clk: 1.9x slower end to end, kept for further work)
+  //   every stage (works; ~10 % slower end to end than the multicast pair at H = 384: kept for further work)
   constexpr bool kCanCluster = TcCfg<H, PREC>::kBlockPipe;
   const int cm = (kCanCluster && tiles >= 2) ? knobs().cluster : 0;
   if (cm == kClusterMcast || cm == kClusterPair) {

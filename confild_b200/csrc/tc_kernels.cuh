@@ -449,6 +449,111 @@ __device__ __forceinline__ void tc_issue_block(int n, uint32_t a_addr, uint32_t 
   e_phase ^= 1u;
 }
 
+// ------------------------------------------------------------------ forward issue stream (round 2)
+// The forward kernels issue a layer's episodes (block n x K slab ks) in the order
+//     for K part kp:  for block n:  (n, 2kp), (n, 2kp+1)
+// i.e. block-major INSIDE a K part.  Block 0's first episodes of the next layer then need only E_0 (K part 0 written,
+// block 0 drained) and run under E_1; block 1's need E_1 to have loaded its accumulator, block 2's E_2 -- in the order
+// the epilogues run -- and in the last K part block 0 completes four episodes before block 2, so E_0 of the next layer
+// starts under the other blocks' MMAs.  (The first version interleaved the blocks slab by slab: (0,ks) (1,ks) (2,ks);
+// its third episode of every layer waited for E_2 to START, which stalled everything queued behind it: the trace showed
+// a 9.6 k clk hole per layer at H = 384.)  Episodes are dealt round-robin to the three issuer warps along ONE global
+// sequence G = 0, 1, 2, ... over all layers and tiles (warp w issues G = w, w+3, ...), so consecutive episodes always
+// come from different warps whatever NB; the commit that completes block n is issued by whichever warp holds the block's
+// last episode (the tensor pipe completes MMAs in issue order).
+template <int H, int PREC, int CM>
+__device__ __forceinline__ void tc_issue_stream(int w, int64_t total_layers, uint32_t a_addr, uint32_t ring_addr,
+                                                uint32_t tmem_d, TcSmemTail* tail, int num_stages) {
+  using C = TcCfg<H, PREC>;
+  constexpr int NB = C::kNBlocks;
+  constexpr int kP = C::kParts;
+  constexpr int kE = C::kSlabs * NB;  // episodes per layer
+  constexpr bool PAIR = (CM == kClusterPair);
+  constexpr uint32_t kM = PAIR ? 2 * kTileM : kTileM;
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(C::kSplit ? 1u : 0u, kM, 128);
+  constexpr uint32_t kIdescF8 = ptx::make_idesc_f8(ptx::kF8E5M2, ptx::kF8E4M3, kM, 128);
+  constexpr int kSlot = tc_slot_bytes(CM);
+  const int64_t total = total_layers * kE;
+  int slot = (w * kP) % num_stages;
+  uint32_t phase = (uint32_t)(((w * kP) / num_stages) & 1);
+  uint32_t turn_phase = w == 0 ? 1u : 0u;  // warp 0 starts (a fresh barrier passes a parity-1 wait)
+#pragma unroll 1
+  for (int64_t G = w; G < total; G += kTcIssuerWarps) {
+    const int64_t layer = G / kE;  // layers issued before this one, over all tiles: parity of the epilogue barriers
+    const int idx = (int)(G - layer * kE);
+    const int kp = idx / (2 * NB), r = idx - kp * 2 * NB, n = r >> 1, ks = 2 * kp + (r & 1);
+    const uint32_t e_phase = (uint32_t)(layer & 1);
+    const uint32_t dcol = tmem_d + n * 128;
+    ptx::mbar_wait<PAIR>(&tail->e_done[kp], e_phase);                              // K part kp of A written
+    if (ks == 0 && n > 0) ptx::mbar_wait<PAIR>(&tail->d_drained[n], e_phase);      // block n in registers
+    {
+      int sl = slot;
+      uint32_t ph = phase;
+#pragma unroll
+      for (int part = 0; part < kP; ++part) {
+        ptx::mbar_wait<PAIR>(&tail->b_full[sl], ph);
+        if (++sl >= num_stages) { sl = 0; ph ^= 1u; }
+      }
+    }
+    ptx::mbar_wait(&tail->turn[w], turn_phase);
+    turn_phase ^= 1u;
+    ptx::tc_fence_after();
+    const bool a_in_tmem = ks < 2 * C::kATmemBlocks;
+    const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
+    const int ss = a_in_tmem ? 0 : ks - 2 * C::kATmemBlocks;
+    const uint64_t a_hi = ptx::make_desc_k_sw128(a_addr + ss * (kTileM * 128));
+    const uint64_t a_lo = ptx::make_desc_k_sw128(a_addr + C::kAPartBytes + ss * (kTileM * 128));
+    if (ptx::elect_one()) {
+      int sl = slot;
+#pragma unroll
+      for (int part = 0; part < kP; ++part) {
+        const uint64_t b = ptx::make_desc_k_sw128(ring_addr + sl * kSlot);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t first = (part == 0) ? (uint32_t)((ks | kk) != 0) : 1u;
+          if (C::kF8 && part == 1) {  // fp8 stage: K = 32 per MMA; e5m2(a_lo) x e4m3(S w), then e5m2(a) x e4m3(S w_lo)
+            if (a_in_tmem) {
+              if (PAIR) ptx::umma_f8_ts_pair(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdescF8, 1u);
+              else ptx::umma_f8_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdescF8, 1u);
+            } else {
+              if (PAIR) ptx::umma_f8_ss_pair(dcol, a_lo + 2 * kk, b + 2 * kk, kIdescF8, 1u);
+              else ptx::umma_f8_ss(dcol, a_lo + 2 * kk, b + 2 * kk, kIdescF8, 1u);
+            }
+          } else if (a_in_tmem) {
+            if (PAIR) {
+              ptx::umma_f16_ts_pair(dcol, at_hi + kk * 8, b + 2 * kk, kIdesc, first);
+              if (C::kSplit && part == 0) ptx::umma_f16_ts_pair(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdesc, 1u);
+            } else {
+              ptx::umma_f16_ts(dcol, at_hi + kk * 8, b + 2 * kk, kIdesc, first);
+              if (C::kSplit && part == 0) ptx::umma_f16_ts(dcol, at_hi + 64 + kk * 8, b + 2 * kk, kIdesc, 1u);
+            }
+          } else {
+            if (PAIR) {
+              ptx::umma_f16_ss_pair(dcol, a_hi + 2 * kk, b + 2 * kk, kIdesc, first);
+              if (C::kSplit && part == 0) ptx::umma_f16_ss_pair(dcol, a_lo + 2 * kk, b + 2 * kk, kIdesc, 1u);
+            } else {
+              ptx::umma_f16_ss(dcol, a_hi + 2 * kk, b + 2 * kk, kIdesc, first);
+              if (C::kSplit && part == 0) ptx::umma_f16_ss(dcol, a_lo + 2 * kk, b + 2 * kk, kIdesc, 1u);
+            }
+          }
+        }
+        if (PAIR) ptx::umma_commit_pair(&tail->b_empty[sl], 0x3);
+        else if (CM == kClusterMcast) ptx::umma_commit_multicast(&tail->b_empty[sl], 0x3);
+        else ptx::umma_commit(&tail->b_empty[sl]);
+        if (++sl >= num_stages) sl = 0;
+      }
+      if (ks == C::kSlabs - 1) {  // the block's last episode: its accumulator is complete
+        if (PAIR) ptx::umma_commit_pair(&tail->d_done[n], 0x3);
+        else ptx::umma_commit(&tail->d_done[n]);
+      }
+      ptx::mbar_arrive(&tail->turn[(w + 1) % kTcIssuerWarps]);
+    }
+    __syncwarp();
+    slot += kTcIssuerWarps * kP;  // this warp's next episode is three episodes further along the ring
+    while (slot >= num_stages) { slot -= num_stages; phase ^= 1u; }
+  }
+}
+
 // ------------------------------------------------------------------ forward
 // STAGE (block pipeline, frame-aligned tiles only): the layer's FiLM shifts are staged in shared memory once per layer
 // instead of being read by every thread with warp-uniform global loads (the H=128 kernel lost 13-20 % without staging).
@@ -696,27 +801,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
       if (PAIR && crank != 0) {
         // peer CTA of a pair: the leader issues the MMAs of both tiles.  One warp here relays "my half of stage s has
         // landed" to the leader's b_full[s] (a bulk copy can only signal a barrier of the CTA it writes to).
-        if (which == 0) {
-          int rs = 0;
-          uint32_t rph = 0;
-          for (int64_t tbase = tile_first; tbase < tile_end; tbase += gridDim.x) {
-            for (int i = 0; i < nl * C::kStagesPerLayer; ++i) {
-              ptx::mbar_wait(&tail->b_full[rs], rph);
-              if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&tail->b_full[rs]), 0));
-              __syncwarp();
-              if (++rs == num_stages) { rs = 0; rph ^= 1u; }
-            }
-          }
+        // Three relay warps, stage q handled by warp q % 3 (one warp alone relays a stage every few hundred clocks).
+        int64_t my_tiles = 0;
+        for (int64_t tbase = tile_first; tbase < tile_end; tbase += gridDim.x) ++my_tiles;
+        const int64_t total = my_tiles * nl * C::kStagesPerLayer;
+        int rs = which % num_stages;
+        uint32_t rph = (uint32_t)((which / num_stages) & 1);
+        for (int64_t q = which; q < total; q += kTcIssuerWarps) {
+          ptx::mbar_wait(&tail->b_full[rs], rph);
+          if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(ptx::smem_u32(&tail->b_full[rs]), 0));
+          __syncwarp();
+          rs += kTcIssuerWarps;
+          while (rs >= num_stages) { rs -= num_stages; rph ^= 1u; }
         }
-      } else if (which < C::kNBlocks) {  // issuer warp n owns accumulator block n (see tc_issue_block)
-        uint32_t turn_phase = which == 0 ? 1u : 0u;  // block 0 first (a fresh barrier passes a parity-1 wait)
-        for (int64_t tbase = tile_first; tbase < tile_end; tbase += gridDim.x) {
-          for (int l = 1; l <= nl; ++l) {
-            tc_issue_block<H, PREC, CM>(which, a_addr, ring_addr, tmem_u, tail, num_stages, slot, b_phase, a_phase,
-                                        turn_phase);
-            if (lane == 0) CNF_TRACE_EVENT(2 + which, 3000 + l);  // block `which` of layer l issued and committed
-          }
-        }
+      } else {  // all three issuer warps share one global episode sequence (tc_issue_stream)
+        int64_t my_tiles = 0;
+        for (int64_t tbase = tile_first; tbase < tile_end; tbase += gridDim.x) ++my_tiles;
+        tc_issue_stream<H, PREC, CM>(which, my_tiles * nl, a_addr, ring_addr, tmem_u, tail, num_stages);
       }
     } else if (which == 0) {
       for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -743,10 +844,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
           for (int s = 0; s < C::kStagesPerLayer; ++s) {
             // image order: K slab -> part -> row block
             int img = s;
-            if (C::kBlockPipe) {  // consumed episode by episode: K slab -> row block n -> part (tc_issue_block)
-              constexpr int NB = C::kNBlocks;
+            if (C::kBlockPipe) {  // consumed episode by episode: K part -> row block n -> slab of the part -> part
+              constexpr int NB = C::kNBlocks;  // (tc_issue_stream)
               const int e = s / C::kParts, part = s % C::kParts;
-              const int ks = e / NB, n = e % NB;
+              const int kp = e / (2 * NB), r = e % (2 * NB), n = r >> 1, ks = 2 * kp + (r & 1);
               img = (ks * C::kParts + part) * NB + n;
             }
             ptx::mbar_wait(&tail->b_empty[slot], phase ^ 1u);

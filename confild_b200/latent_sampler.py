@@ -277,7 +277,7 @@ def sample_latents(model: nn.Module, shape: Sequence[int], steps: int = 1000, no
     def one_step():
         eps = unet(x_static, t_dev)
         noise = torch.randn_like(x_static)
-        x_static.copy_(ddpm_step(eps, x_static, table[t_dev[0]], noise))
+        x_static.copy_(ddpm_step(eps, x_static, table.index_select(0, t_dev), noise))  # (B, 5) rows: no host sync
         t_dev.sub_(1)
 
     side = torch.cuda.Stream(device=dev)
