@@ -43,6 +43,7 @@ MUFU_PEAK_SIN_PER_S = 4.625e12
 #: capture of this command (not measured inside this run): {precision: (bytes, profile file)}
 NCU_TRAFFIC_OFFLINE = {
     "bf16x3": (771521280, "profiles/r01_ncu_tc2_forward_case1_bf16x3_benchsize_final.txt"),
+    "f16f8": (776403968, "profiles/r02_ncu_tc2_forward_case1_f16f8_benchsize.txt"),  # 16.25 MB read + 760.15 MB written
 }
 
 
