@@ -65,7 +65,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       const uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000ull) {  // 4 s without progress: a protocol bug, fail the launch instead of hanging
-        printf("cnf: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+        printf("cnf: mbarrier wait timed out (block %d thread %d, barrier at shared 0x%x, parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, smem_u32(bar), parity);
+        while (global_timer_ns() - now < 1000000000ull) {}  // let the other stuck waiters report before the launch dies
         __trap();
       }
     }
