@@ -63,7 +63,6 @@ Knobs& mutable_knobs() {
     k.stages = env_int("CNF_TC_STAGES", 0);
     k.packed = env_int("CNF_TC_PACKED", -1);
     k.cluster = env_int("CNF_TC_CLUSTER", 1);
-    k.tc3 = env_int("CNF_TC3", 0);
   });
   return k;
 }
@@ -75,7 +74,6 @@ int set_knob(const char* name, int value) {
   else if (!strcmp(name, "CNF_TC_STAGES")) k.stages = value;
   else if (!strcmp(name, "CNF_TC_PACKED")) k.packed = value;
   else if (!strcmp(name, "CNF_TC_CLUSTER")) k.cluster = value;
-  else if (!strcmp(name, "CNF_TC3")) k.tc3 = value;
   else return fail(CNF_ERR_INVALID_ARGUMENT, "unknown debug knob %s", name);
   return CNF_OK;
 }
@@ -123,11 +121,7 @@ int tc_forward_dispatch(int precision, const FwdArgs& a) {
   if (use_tc2(a.d)) {
     switch (precision) {
       case CNF_PREC_BF16X3: return cnf::host::tc2_forward_bf16x3(a);
-      case CNF_PREC_F16F8:
-        // inference on frame-aligned tiles with a single target: three tile slots per SM
-        if (cnf::host::knobs().tc3 != 0 && !a.stash && a.outs.n == 1 && !cnf::host::use_packed(a.P))
-          return cnf::host::tc3_forward_f16f8(a);
-        return cnf::host::tc2_forward_f16f8(a);
+      case CNF_PREC_F16F8: return cnf::host::tc2_forward_f16f8(a);
       default: return cnf::host::tc2_forward_fp16(a);
     }
   }
@@ -212,7 +206,6 @@ extern "C" int cnf_debug_set_trace(void* d_buf) {
   rc |= cnf::host::set_trace_tc2_fwd_bf16x3(p);
   rc |= cnf::host::set_trace_tc2_fwd_fp16(p);
   rc |= cnf::host::set_trace_tc2_fwd_f16f8(p);
-  rc |= cnf::host::set_trace_tc3_fwd_f16f8(p);
   rc |= cnf::host::set_trace_tc_fwd_f16f8(p);
   rc |= cnf::host::set_trace_tc2_bwd(p);
   rc |= cnf::host::set_trace_tc_fwd_bf16x3(p);

@@ -41,7 +41,6 @@ struct Knobs {
   int tc2 = 1;
   int stages = 0;
   int packed = -1;
-  int tc3 = 0;      // CNF_TC3: H = 128 f16f8 inference on the three-slot kernel (tc3_kernels.cuh)
   int cluster = 1;  // CNF_TC_CLUSTER: H = 256/384 forward as CTA pairs: 1 = multicast weight stages (default), 2 = cta_group::2 MMAs, 0 = single CTAs
 };
 const Knobs& knobs();
@@ -94,7 +93,6 @@ struct BwdArgs {
 int tc2_forward_bf16x3(const FwdArgs& a);
 int tc2_forward_fp16(const FwdArgs& a);
 int tc2_forward_f16f8(const FwdArgs& a);
-int tc3_forward_f16f8(const FwdArgs& a);  // three tile slots per SM (inference, frame-aligned tiles, one target)
 int tc2_backward(const BwdArgs& a);
 int tc_forward_bf16x3(const FwdArgs& a);
 int tc_forward_fp16(const FwdArgs& a);
@@ -116,7 +114,6 @@ inline int ensure_smem(Kernel kern, size_t smem, int device, std::atomic<size_t>
 int set_trace_tc2_fwd_bf16x3(unsigned long long* p);
 int set_trace_tc2_fwd_fp16(unsigned long long* p);
 int set_trace_tc2_fwd_f16f8(unsigned long long* p);
-int set_trace_tc3_fwd_f16f8(unsigned long long* p);
 int set_trace_tc_fwd_f16f8(unsigned long long* p);
 int set_trace_tc2_bwd(unsigned long long* p);
 int set_trace_tc_fwd_bf16x3(unsigned long long* p);

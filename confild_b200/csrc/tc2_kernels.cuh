@@ -40,6 +40,7 @@ struct Tc2SmemTail {
   uint64_t b_full[kTcMaxStages];
   uint64_t b_empty[kTcMaxStages];
   uint64_t a_half[2];  // K slab 0 of the slot's A operand written and its accumulator drained (forward kernel)
+  uint64_t a_q3[2];    // ... and columns 64-95 (the first half of K slab 1): forward kernel only
   uint64_t a_full[2];
   uint64_t d_full[2];
   uint64_t turn[2];  // issue token passed between the two MMA issuer warps
@@ -123,9 +124,15 @@ __device__ __forceinline__ void tc2_store_a16(uint32_t tmem_a, int c0, const flo
 }
 
 // Columns of a warpgroup (column half hf), in the order it produces them: groups 0,1 lie in K slab 0 of the next
-// layer's A operand (columns 0-63), groups 2,3 in K slab 1, so the first half of the next layer's MMAs can start
-// when every warp is half-way through its epilogue.
-__device__ __forceinline__ constexpr int tc2_group_col(int hf, int c) { return 32 * hf + 16 * (c & 1) + 64 * (c >> 1); }
+// layer's A operand (columns 0-63), so the first half of the next layer's MMAs can start when every warp is half-way
+// through its epilogue; group 2 of the two warpgroups together covers columns 64-95 and group 3 columns 96-127, so
+// the MMAs of K slab 1 go out in two quarters and only the last quarter trails the epilogue.
+__device__ __forceinline__ constexpr int tc2_group_col(int hf, int c) {
+  return c < 2 ? 32 * hf + 16 * c : 64 + 32 * (c - 2) + 16 * hf;
+}
+// Quarter issue of K slab 1 pays where the tensor pipe has slack: fp16 (8 MMAs per slot-layer) +8 %; f16f8 (16) +-0;
+// bf16x3 (24, tensor-bound) -5 % -- measured on case1, 1,024 x 65,536.
+__host__ __device__ constexpr bool tc2_quarter_issue(int prec) { return prec == CNF_PREC_FP16; }
 
 // One hidden layer for this thread's row and its warpgroup's 64 columns.
 // Software pipeline over four 16-column groups: the TMEM load of group c+2 and the sines (MUFU) of group c+1 are issued
@@ -139,7 +146,8 @@ template <int PREC, bool LAST, bool STASH, typename HalfHook = Tc2NoHook>
 __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tmem_a, int hf,
                                                  const float* __restrict__ sbuf, const float* __restrict__ w_out_s,
                                                  int cout, float (&y)[4], __half* stash_l, uint64_t* a_half,
-                                                 uint64_t* a_full, float inv = 1.f, HalfHook on_half = HalfHook()) {
+                                                 uint64_t* a_q3, uint64_t* a_full, float inv = 1.f,
+                                                 HalfHook on_half = HalfHook()) {
   constexpr bool SCALED = (PREC == CNF_PREC_F16F8);
   uint32_t v[2][16];
   float hcur[16], hnext[16];
@@ -167,6 +175,10 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
         ptx::tc_fence_before();
         ptx::mbar_arrive(a_half);
         on_half();  // debug trace hook (empty in product builds)
+      } else if (c == 2 && tc2_quarter_issue(PREC)) {
+        ptx::tmem_wait_st();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(a_q3);
       } else if (c == 3) {
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
@@ -240,6 +252,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
     }
     for (int g = 0; g < 2; ++g) {
       ptx::mbar_init(&tail->a_half[g], 256);
+      ptx::mbar_init(&tail->a_q3[g], 256);
       ptx::mbar_init(&tail->a_full[g], 256);
       ptx::mbar_init(&tail->d_full[g], 2);  // one commit per issuer warp (K slab 0, K slab 1)
       ptx::mbar_init(&tail->turn[g], 1);
@@ -333,6 +346,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         }
         ptx::tmem_wait_st();
         ptx::tc_fence_before();
+        if (half == 1 && tc2_quarter_issue(PREC)) ptx::mbar_arrive(&tail->a_q3[g]);
         ptx::mbar_arrive(half == 0 ? &tail->a_half[g] : &tail->a_full[g]);  // K slab `half` of the A operand is in TMEM
       }
       if (tracer) CNF_TRACE_EVENT(trole, 101);  // layer 0 done, a_full arrived
@@ -366,11 +380,11 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         if (!PACKED)
           tc2_hidden_layer<PREC, false, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][l & 1], tail->w_out_s, cout, y,
                                                STASH ? st_row + (size_t)l * H * kTileM : nullptr, &tail->a_half[g],
-                                               &tail->a_full[g], inv, half_hook);
+                                               &tail->a_q3[g], &tail->a_full[g], inv, half_hook);
         else
           tc2_hidden_layer<PREC, false, STASH>(lane_base, tmem_a, hf, sh + (size_t)l * H, tail->w_out_s, cout, y,
                                                STASH ? st_row + (size_t)l * H * kTileM : nullptr, &tail->a_half[g],
-                                               &tail->a_full[g], inv, half_hook);
+                                               &tail->a_q3[g], &tail->a_full[g], inv, half_hook);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + l);  // epilogue of layer l done
       }
       {
@@ -378,10 +392,10 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         const float inv = kF8 ? tail->inv_scale[nl - 1] : 1.f;
         if (!PACKED)
           tc2_hidden_layer<PREC, true, STASH>(lane_base, tmem_a, hf, tail->shift_s[g][nl & 1], tail->w_out_s, cout, y,
-                                              STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr, nullptr, inv);
+                                              STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr, nullptr, nullptr, inv);
         else
           tc2_hidden_layer<PREC, true, STASH>(lane_base, tmem_a, hf, sh + (size_t)nl * H, tail->w_out_s, cout, y,
-                                              STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr, nullptr, inv);
+                                              STASH ? st_row + (size_t)nl * H * kTileM : nullptr, nullptr, nullptr, nullptr, inv);
         if (tracer) CNF_TRACE_EVENT(trole, 400 + nl);
       }
       // ---- head: combine the two column halves, 12-byte store per point
@@ -441,6 +455,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
     // when both halves of the layer have finished.
     const int half = warp - kMmaWarp;
     constexpr int kSPH = kSPL / 2;  // stages per half: hi, lo of one K slab (one stage for fp16)
+    constexpr bool kQuarter = tc2_quarter_issue(PREC);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t ring_addr = ptx::smem_u32(ring);
     uint32_t a_phase[2] = {0u, 0u};
@@ -464,41 +479,61 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
           const bool mine = (2 * pair + g < tiles);  // an odd tile count leaves slot 1 idle in the last pair
           const uint32_t tmem_d = tmem_u + g * kTc2SlotCols;
           const uint32_t tmem_a = tmem_d + 128;
+          // The K steps of this warp's stages: all four of each stage (q < 0), or those of the 32-column quarter q of
+          // the slab (16-bit stages: steps 2q, 2q+1; the fp8 stage: step q of e5m2(a_lo) and step 2+q of e5m2(a)).
+          auto issue = [&](int q, bool release) {
+            int slot = slot0;
+#pragma unroll
+            for (int s = 0; s < kSPH; ++s) {
+              const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
+              const int part = s % kParts;
+              const bool f8part = kF8 && part == 1;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                if (q >= 0 && (f8part ? (kk & 1) : (kk >> 1)) != q) continue;
+                const uint32_t a_hi = tmem_a + (half * 4 + kk) * 8;  // 16 K elements = 8 packed columns
+                if (part == 0) {
+                  ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (uint32_t)((half | kk) != 0));
+                  if (kSplit) ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
+                } else if (kF8) {  // 32 8-bit K elements = 8 packed columns of this K slab's fp8 operand
+                  ptx::umma_f8_ts(tmem_d, tmem_a + 64 + half * 32 + kk * 8, b + 2 * kk, kIdescF8, 1u);
+                } else {
+                  ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
+                }
+              }
+              if (release) ptx::umma_commit(&tail->b_empty[slot]);  // (tracks every earlier MMA of this thread)
+              if (++slot >= num_stages) slot = 0;
+            }
+          };
           if (mine) {
             if (lane == 0) CNF_TRACE_EVENT(2 + half, 1000 + 500 * g + l);  // start waiting for the A operand
-            ptx::mbar_wait(half == 0 ? &tail->a_half[g] : &tail->a_full[g], a_phase[g]);
-            a_phase[g] ^= 1u;
+            ptx::mbar_wait(half == 0 ? &tail->a_half[g] : kQuarter ? &tail->a_q3[g] : &tail->a_full[g], a_phase[g]);
             if (lane == 0) CNF_TRACE_EVENT(2 + half, 2000 + 500 * g + l);  // operands ready
           }
           ptx::mbar_wait(&tail->turn[half], turn_phase);
           turn_phase ^= 1u;
           ptx::tc_fence_after();
+          if (kQuarter && half == 1 && mine) {
+            // K slab 1 in two quarters: columns 64-95 now, 96-127 when the epilogue is complete.  This warp is held
+            // back until the tensor pipe has taken the first quarter, well within the epilogue's last column group.
+            if (ptx::elect_one()) issue(0, false);
+            __syncwarp();
+            ptx::mbar_wait(&tail->a_full[g], a_phase[g]);
+            ptx::tc_fence_after();
+          }
+          if (mine) a_phase[g] ^= 1u;
           if (ptx::elect_one()) {
-            int slot = slot0;
+            if (mine) {
+              issue(kQuarter && half == 1 ? 1 : -1, true);
+              ptx::umma_commit(&tail->d_full[g]);
+            } else {
+              int slot = slot0;
 #pragma unroll
-            for (int s = 0; s < kSPH; ++s) {
-              if (mine) {
-                const uint64_t b = ptx::make_desc_k_sw128(ring_addr + slot * kStageBytes);
-                const int part = s % kParts;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const uint32_t a_hi = tmem_a + (half * 4 + kk) * 8;  // 16 K elements = 8 packed columns
-                  if (part == 0) {
-                    ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, (uint32_t)((half | kk) != 0));
-                    if (kSplit) ptx::umma_f16_ts(tmem_d, a_hi + 64, b + 2 * kk, kIdesc, 1u);
-                  } else if (kF8) {  // 32 8-bit K elements = 8 packed columns of this K slab's fp8 operand
-                    ptx::umma_f8_ts(tmem_d, tmem_a + 64 + half * 32 + kk * 8, b + 2 * kk, kIdescF8, 1u);
-                  } else {
-                    ptx::umma_f16_ts(tmem_d, a_hi, b + 2 * kk, kIdesc, 1u);
-                  }
-                }
-                ptx::umma_commit(&tail->b_empty[slot]);
-              } else {
+              for (int s = 0; s < kSPH; ++s) {
                 ptx::mbar_arrive(&tail->b_empty[slot]);  // idle slot: still release its share of the stage
+                if (++slot >= num_stages) slot = 0;
               }
-              if (++slot >= num_stages) slot = 0;
             }
-            if (mine) ptx::umma_commit(&tail->d_full[g]);
             ptx::mbar_arrive(&tail->turn[half ^ 1]);
           }
           __syncwarp();
