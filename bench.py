@@ -353,7 +353,9 @@ def measure_dps(cb, model, dims, case, dev, args, iters):
         torch.autograd.grad(norm, l)
 
     res = {"workload": f"{case} shapes, {Td} latents x {Pd} points, {S} random sensors, forward(+cos stash) + loss + "
-                       "backward to dL/dlatent (BASELINE config 4)", "precision": model.precision}
+                       "backward to dL/dlatent (BASELINE config 4)", "precision": model.precision,
+           "backward_precision": "fp32" if model.resolved_precision == "fp32" else
+           "bf16x3 (the backward always runs the bf16 hi/lo split on the fp16 cos stash, whatever the forward mode)"}
     for name, fn, rows in (("autograd_dense", autograd_step, Td * Pd), ("fused_loss_dense", fused_step, Td * Pd),
                            ("fused_loss_dense_zero_row_skip", fused_skip_step, Td * Pd),
                            ("sensor_compacted", compact_step, Td * S)):

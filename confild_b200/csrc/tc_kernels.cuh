@@ -477,6 +477,8 @@ __device__ __forceinline__ void tc_issue_stream(int w, int64_t total_layers, uin
   int slot = (w * kP) % num_stages;
   uint32_t phase = (uint32_t)(((w * kP) / num_stages) & 1);
   uint32_t turn_phase = w == 0 ? 1u : 0u;  // warp 0 starts (a fresh barrier passes a parity-1 wait)
+  CNF_TRACE_DECL;
+  [[maybe_unused]] const bool tracer = (threadIdx.x & 31) == 0;
 #pragma unroll 1
   for (int64_t G = w; G < total; G += kTcIssuerWarps) {
     const int64_t layer = G / kE;  // layers issued before this one, over all tiles: parity of the epilogue barriers
@@ -484,8 +486,10 @@ __device__ __forceinline__ void tc_issue_stream(int w, int64_t total_layers, uin
     const int kp = idx / (2 * NB), r = idx - kp * 2 * NB, n = r >> 1, ks = 2 * kp + (r & 1);
     const uint32_t e_phase = (uint32_t)(layer & 1);
     const uint32_t dcol = tmem_d + n * 128;
+    if (tracer) CNF_TRACE_EVENT(20 + w, 100000 + layer * 100 + idx);               // episode: start waiting
     ptx::mbar_wait<PAIR>(&tail->e_done[kp], e_phase);                              // K part kp of A written
     if (ks == 0 && n > 0) ptx::mbar_wait<PAIR>(&tail->d_drained[n], e_phase);      // block n in registers
+    if (tracer) CNF_TRACE_EVENT(20 + w, 200000 + layer * 100 + idx);               // A operand / accumulator ready
     {
       int sl = slot;
       uint32_t ph = phase;
@@ -495,9 +499,11 @@ __device__ __forceinline__ void tc_issue_stream(int w, int64_t total_layers, uin
         if (++sl >= num_stages) { sl = 0; ph ^= 1u; }
       }
     }
+    if (tracer) CNF_TRACE_EVENT(20 + w, 300000 + layer * 100 + idx);  // weight stages landed
     ptx::mbar_wait(&tail->turn[w], turn_phase);
     turn_phase ^= 1u;
     ptx::tc_fence_after();
+    if (tracer) CNF_TRACE_EVENT(20 + w, 400000 + layer * 100 + idx);  // issue token received
     const bool a_in_tmem = ks < 2 * C::kATmemBlocks;
     const uint32_t at_hi = tmem_d + H + (ks / 2) * 128 + (ks & 1) * 32;
     const int ss = a_in_tmem ? 0 : ks - 2 * C::kATmemBlocks;
@@ -549,6 +555,7 @@ __device__ __forceinline__ void tc_issue_stream(int w, int64_t total_layers, uin
       ptx::mbar_arrive(&tail->turn[(w + 1) % kTcIssuerWarps]);
     }
     __syncwarp();
+    if (tracer) CNF_TRACE_EVENT(20 + w, 500000 + layer * 100 + idx);  // episode issued
     slot += kTcIssuerWarps * kP;  // this warp's next episode is three episodes further along the ring
     while (slot >= num_stages) { slot -= num_stages; phase ^= 1u; }
   }
