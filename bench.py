@@ -544,7 +544,8 @@ def measure_config5(cb, model, dev, world, rank, args):
                         f"(1,{Tl},{Ll}) latent image with the case1 U-Net (92 M parameters, random init), then CNF decode of "
                         f"{frames} frames x {POINTS} points to pinned host memory",
             "sampler_s": t_sample, "sampler_ms_per_step": t_sample / steps * 1e3,
-            "sampler": "bf16 autocast, fused attention, channels-last, one step captured in a CUDA graph",
+            "sampler": "LatentUNet.forward_inference: bf16 channels-last end to end, GroupNorm(+embedding add)+SiLU as the "
+                       "library's cnf_group_norm_nhwc_bf16 kernels, fused attention, one step captured in a CUDA graph",
             "sampler_eager_fp32_ms_per_step": t_eager_step * 1e3,
             "sampler_speedup_vs_eager_fp32": t_eager_step / (t_sample / steps),
             "decode_s": t_decode, "decode_point_frames_per_s": frames * POINTS / t_decode, "unit": UNIT,

@@ -22,9 +22,9 @@ EXPORTS = [
     "cnf_abi_version", "cnf_last_error", "cnf_tc_supported", "cnf_param_count", "cnf_packed_bytes",
     "cnf_pack_weights", "cnf_film_shift", "cnf_stash_bytes", "cnf_forward", "cnf_forward_gather", "cnf_backward",
     "cnf_film_shift_backward", "cnf_film_shift_backward_scaled", "cnf_forward_loss", "cnf_query_launch",
-    "cnf_set_debug_knob",
+    "cnf_set_debug_knob", "cnf_group_norm_scratch_bytes", "cnf_group_norm_nhwc_bf16",
 ]
-ABI_VERSION = 2
+ABI_VERSION = 3
 LOSS_PARTIALS = 4096  # CNF_LOSS_PARTIALS
 
 
@@ -105,6 +105,10 @@ def load() -> ctypes.CDLL:
     lib.cnf_forward_loss.argtypes = [dp, vp, i32, vp, i64, vp, vp, i64, i64, vp, sz, ctypes.POINTER(CnfSensorLoss), vp]
     lib.cnf_query_launch.restype = i32
     lib.cnf_query_launch.argtypes = [dp, i32, i64, i64, ctypes.POINTER(i64), i32]
+    lib.cnf_group_norm_scratch_bytes.restype = sz
+    lib.cnf_group_norm_scratch_bytes.argtypes = [i64]
+    lib.cnf_group_norm_nhwc_bf16.restype = i32
+    lib.cnf_group_norm_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, f32, i32, vp]
     if lib.cnf_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path}: ABI version {lib.cnf_abi_version()} != {ABI_VERSION}; rebuild with "
                            "`python -m confild_b200.build --force`")

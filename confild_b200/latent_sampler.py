@@ -19,8 +19,13 @@ is the B200-side replacement of that outer loop around the CNF decoder:
 * ``generate_fields`` -- sampler -> latent de-normalisation -> batched CNF decode through ``confild_b200.decoder``: the
   batched replacement of the ``B*T`` one-frame Python iterations of ``scripts/inference.py:71-79``.
 
-This is host-side PyTorch around the hot path (the U-Net is outside the graded kernel set); its kernels are library
-kernels (cuDNN / cuBLAS / flash attention).
+This is host-side PyTorch around the hot path (the U-Net is outside the graded kernel set); its GEMM-shaped kernels are
+library kernels (cuDNN / cuBLAS / flash attention).  ``LatentUNet.forward_inference`` is the no-grad fast path the
+sampler uses on CUDA: bf16 channels-last activations end to end, weights cast once, and every GroupNorm(+SiLU) site --
+including the residual block's timestep-embedding add in front of the second one -- as one call of the library's
+``cnf_group_norm_nhwc_bf16`` (``csrc/unet_ops.cu``) instead of the eager ``float() / native_group_norm / to(bf16) /
+SiLU`` chain and the NCHW<->NHWC conversions cuDNN then runs around every convolution (a profile of the autocast path
+shows the convolutions at ~10 % of the step; normalisation, layout conversions and element-wise passes take the rest).
 """
 from __future__ import annotations
 
@@ -31,6 +36,36 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+from . import _native
+
+
+def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, num_groups: int, eps: float = 1e-5,
+                    add: Optional[torch.Tensor] = None, silu: bool = False) -> torch.Tensor:
+    """``act(GroupNorm(x + add[:, :, None, None]))`` for a CUDA bf16 channels-last ``x (N, C, H, W)`` with fp32
+    statistics (``cnf_group_norm_nhwc_bf16``); ``weight`` / ``bias`` fp32 ``(C,)``, ``add`` fp32 ``(N, C)`` or None.
+    Inference only (no autograd).  Reference semantics: src/nn.py:17-19 (GroupNorm32) followed by nn.SiLU."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+        raise ValueError("group_norm_nhwc expects a 4-d CUDA bfloat16 tensor")
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    N, C, H, W = x.shape
+    if weight.dtype != torch.float32 or bias.dtype != torch.float32 or weight.numel() != C or bias.numel() != C:
+        raise ValueError("group_norm_nhwc: weight and bias must be float32 of shape (C,)")
+    if add is not None:
+        if add.dtype != torch.float32 or tuple(add.shape) != (N, C):
+            raise ValueError("group_norm_nhwc: add must be float32 of shape (N, C)")
+        add = add.contiguous()
+    lib = _native.load()
+    y = torch.empty_like(x)  # preserves the channels-last strides
+    scratch = torch.empty(max(1, lib.cnf_group_norm_scratch_bytes(N) // 4), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _native.check(lib.cnf_group_norm_nhwc_bf16(x.data_ptr(), None if add is None else add.data_ptr(),
+                                                   weight.contiguous().data_ptr(), bias.contiguous().data_ptr(),
+                                                   y.data_ptr(), scratch.data_ptr(), N, H * W, C, int(num_groups),
+                                                   float(eps), int(bool(silu)), stream), "cnf_group_norm_nhwc_bf16")
+    return y
 
 
 # ------------------------------------------------------------------------------------------ U-Net
@@ -184,6 +219,88 @@ class LatentUNet(nn.Module):
         self.out = nn.Sequential(_GroupNorm32(32, ch), nn.SiLU(),
                                  _zeroed(nn.Conv2d(int(mult[0] * mc), out_channels, 3, padding=1)))
 
+    # ------------------------------------------------------------------ inference fast path (CUDA, no autograd)
+    @torch.no_grad()
+    def prepare_inference(self) -> "LatentUNet":
+        """(Re)build the bf16 / channels-last weight copies ``forward_inference`` uses (call again after changing or
+        loading weights; ``sample_latents`` does so on every call)."""
+        bf = torch.bfloat16
+        fast = {}
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                fast[m] = (m.weight.detach().to(bf).contiguous(memory_format=torch.channels_last), m.bias.detach().to(bf))
+            elif isinstance(m, nn.Conv1d):  # 1x1: a linear layer over the channels
+                fast[m] = (m.weight.detach()[:, :, 0].to(bf).contiguous(), m.bias.detach().to(bf))
+            elif isinstance(m, nn.Linear):
+                fast[m] = (m.weight.detach().to(bf).contiguous(), m.bias.detach().to(bf))
+            elif isinstance(m, nn.GroupNorm):
+                fast[m] = (m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous())
+        self._fast = fast
+        return self
+
+    @torch.no_grad()
+    def forward_inference(self, x, timesteps):
+        """Same function as ``forward`` under bf16 autocast, for CUDA inference: see the module docstring."""
+        fast = getattr(self, "_fast", None)
+        if fast is None:
+            fast = self.prepare_inference()._fast
+        bf, cl = torch.bfloat16, torch.channels_last
+
+        def lin(m, v):
+            w, b = fast[m]
+            return F.linear(v, w, b)
+
+        def conv(m, v):
+            w, b = fast[m]
+            return F.conv2d(v, w, b, m.stride, m.padding).contiguous(memory_format=cl)
+
+        def gn(m, v, silu, add=None):
+            w, b = fast[m]
+            return group_norm_nhwc(v, w, b, m.num_groups, m.eps, add=add, silu=silu)
+
+        emb = lin(self.time_embed[2], F.silu(lin(self.time_embed[0], sinusoidal_embedding(timesteps, self.model_channels).to(bf))))
+        emb_act = F.silu(emb)  # every residual block starts its embedding branch with the same SiLU
+
+        def res(m, v):
+            h = conv(m.in_layers[2], gn(m.in_layers[0], v, True))
+            e = lin(m.emb_layers[1], emb_act).float()  # added inside the second normalisation, in fp32
+            h = conv(m.out_layers[3], gn(m.out_layers[0], h, True, add=e))
+            return (v if isinstance(m.skip_connection, nn.Identity) else conv(m.skip_connection, v)) + h
+
+        def attn(m, v):
+            n, c, hh, ww = v.shape
+            t = hh * ww
+            heads = m.num_heads
+            xn = gn(m.norm, v, False).permute(0, 2, 3, 1).reshape(n, t, c)  # a view: the memory is (n, t, c) already
+            qkv = lin(m.qkv, xn).reshape(n, t, heads, 3, c // heads)       # legacy order: per head [q | k | v]
+            q, k, vv = (qkv[:, :, :, i].transpose(1, 2) for i in range(3))  # (n, heads, t, ch)
+            a = F.scaled_dot_product_attention(q, k, vv).transpose(1, 2).reshape(n, t, c)
+            return v + lin(m.proj_out, a).reshape(n, hh, ww, c).permute(0, 3, 1, 2)
+
+        def stage(blk, v):
+            for layer in blk:
+                if isinstance(layer, _Res):
+                    v = res(layer, v)
+                elif isinstance(layer, _Attn):
+                    v = attn(layer, v)
+                elif isinstance(layer, _Down):
+                    v = conv(layer.op, v)
+                elif isinstance(layer, _Up):
+                    v = conv(layer.conv, F.interpolate(v, scale_factor=2, mode="nearest"))
+                else:
+                    v = conv(layer, v)
+            return v
+
+        h = x.to(bf).contiguous(memory_format=cl)
+        hs = []
+        for blk in self.input_blocks:
+            h = stage(blk, h)
+            hs.append(h)
+        h = stage(self.middle_block, h)
+        for blk in self.output_blocks:
+            h = stage(blk, torch.cat([h, hs.pop()], dim=1).contiguous(memory_format=cl))
+        return conv(self.out[2], gn(self.out[0], h, True)).to(x.dtype).contiguous()
+
     def forward(self, x, timesteps):
         """``x (N, C, T, L)``, ``timesteps (N,)`` -> predicted noise ``(N, C, T, L)`` (reference: unet.py:634-663)."""
         emb = self.time_embed(sinusoidal_embedding(timesteps, self.model_channels))
@@ -244,11 +361,12 @@ def ddpm_step(eps: torch.Tensor, x: torch.Tensor, coef: torch.Tensor, noise: tor
 @torch.no_grad()
 def sample_latents(model: nn.Module, shape: Sequence[int], steps: int = 1000, noise_schedule: str = "cosine",
                    device=None, autocast_dtype: Optional[torch.dtype] = torch.bfloat16, use_cuda_graph: bool = True,
-                   generator: Optional[torch.Generator] = None) -> torch.Tensor:
+                   generator: Optional[torch.Generator] = None, fast_unet: bool = True) -> torch.Tensor:
     """Ancestral sampling ``p_sample_loop(model, shape)`` (gaussian_diffusion.py:441-535) -> ``(B, C, T, L)`` in [-1, 1].
 
     On a CUDA device one step (U-Net under ``autocast_dtype``, update, fresh noise) is captured in a CUDA graph and
-    replayed ``steps`` times; the timestep is a device counter, so the host only enqueues replays.  ``generator`` makes
+    replayed ``steps`` times; the timestep is a device counter, so the host only enqueues replays.  With
+    ``fast_unet`` (default) and bf16 the U-Net runs ``LatentUNet.forward_inference`` instead of ``forward`` under autocast.  ``generator`` makes
     the eager path reproducible (graph capture uses the default CUDA generator, which is graph-safe).
     """
     dev = torch.device(device) if device is not None else next(model.parameters()).device
@@ -258,7 +376,13 @@ def sample_latents(model: nn.Module, shape: Sequence[int], steps: int = 1000, no
     x = torch.randn(*shape, device=dev, generator=generator)
     cuda = dev.type == "cuda"
 
+    fast = (cuda and fast_unet and autocast_dtype == torch.bfloat16 and hasattr(model, "forward_inference"))
+    if fast:
+        model.prepare_inference()  # bf16 channels-last weight copies, rebuilt here so that they are never stale
+
     def unet(xx, tt):
+        if fast:
+            return model.forward_inference(xx, tt)
         if cuda and autocast_dtype is not None:
             with torch.autocast("cuda", dtype=autocast_dtype):
                 return model(xx.contiguous(memory_format=torch.channels_last), tt).float()

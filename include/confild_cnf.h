@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define CNF_ABI_VERSION 2
+#define CNF_ABI_VERSION 3
 
 /* error codes */
 #define CNF_OK 0
@@ -178,6 +178,21 @@ int cnf_forward_loss(const cnf_dims* dims, const void* d_packed, int precision, 
  *   [2] threads per CTA, [3] dynamic shared memory bytes per CTA, [4] resident CTAs per SM,
  *   [5] TMEM columns per CTA (0 for the CUDA-core path), [6] points per tile. */
 int cnf_query_launch(const cnf_dims* dims, int precision, int64_t T, int64_t P, int64_t* values, int n);
+
+/* ---- sampler-side helper (not part of the decode path) ------------------------------------------
+ * GroupNorm over channels-last bf16 activations with fp32 statistics, an optional per-(sample, channel) value added
+ * before the normalisation (the residual block's timestep-embedding add) and an optional SiLU:
+ *     y[n,p,c] = act( ((x[n,p,c] + add[n,c]) - mean[n,g]) * rstd[n,g] * gamma[c] + beta[c] ),   g = c / (C/groups)
+ * x, y: (N, HW, C) bf16 = a torch channels_last (N,C,H,W) tensor, 16-byte aligned, C a multiple of 8 and of `groups`
+ * (<= 64); d_add NULL or (N, C) fp32; d_partials: scratch of cnf_group_norm_scratch_bytes(N) bytes.  Deterministic
+ * (no atomics).  Replaces GroupNorm32 + SiLU of the guided-diffusion U-Net's blocks
+ * (UnconditionalDiffusionTraining_and_Generation/src/nn.py:17-19, src/unet.py:185-200,228-256,283-300) in the
+ * inference-only fast path of confild_b200.LatentUNet. */
+#define CNF_GN_MAX_CHUNKS 128
+size_t cnf_group_norm_scratch_bytes(int64_t N);
+int cnf_group_norm_nhwc_bf16(const void* d_x, const float* d_add, const float* d_gamma, const float* d_beta, void* d_y,
+                             float* d_partials, int64_t N, int64_t HW, int32_t C, int32_t groups, float eps,
+                             int32_t silu, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ def lib():
 
 def test_header_symbols_are_exported(lib):
     header = open(os.path.join(ROOT, "include", "confild_cnf.h")).read()
-    declared = set(re.findall(r"^\s*(?:const\s+char\s*\*|int)\s+(cnf_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:const\s+char\s*\*|int|size_t)\s+(cnf_\w+)\s*\(", header, flags=re.M))
     assert declared == set(_native.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name

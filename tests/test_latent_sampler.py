@@ -122,6 +122,95 @@ def test_fast_path_matches_fp32_eager_and_graph_sampler_runs():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 128, 128, 128), (2, 512, 8, 8), (3, 896, 16, 16), (1, 640, 5, 7), (2, 64, 1, 1),
+                                   (2, 384, 32, 32)])
+@pytest.mark.parametrize("silu,with_add", [(True, False), (True, True), (False, False)])
+def test_group_norm_nhwc_kernel_vs_torch(shape, silu, with_add):
+    """cnf_group_norm_nhwc_bf16 against F.group_norm in fp32 on the same bf16 inputs (GroupNorm32 + SiLU, nn.py:17-19);
+    tolerance = bf16 output rounding (2^-8 relative) + the fast exp."""
+    from confild_b200.latent_sampler import group_norm_nhwc
+    import torch.nn.functional as F
+
+    N, C, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(N * 1000 + C)
+    x = (torch.randn(N, C, H, W, device="cuda", generator=g) * 1.7 + 0.3).to(torch.bfloat16)
+    x = x.contiguous(memory_format=torch.channels_last)
+    w = torch.randn(C, device="cuda", generator=g)
+    b = torch.randn(C, device="cuda", generator=g)
+    add = torch.randn(N, C, device="cuda", generator=g) if with_add else None
+    xin = x.float() + (add[:, :, None, None] if with_add else 0.0)
+    if H * W * (C // 32) > 1:
+        want = F.group_norm(xin, 32, w, b, 1e-5)
+    else:  # a group of one element normalises to beta
+        want = b[None, :, None, None].expand(N, C, H, W).clone()
+    if silu:
+        want = F.silu(want)
+    got = group_norm_nhwc(x, w, b, 32, 1e-5, add=add, silu=silu)
+    assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
+    got2 = group_norm_nhwc(x, w, b, 32, 1e-5, add=add, silu=silu)
+    assert torch.equal(got, got2)  # deterministic: no atomics
+    err = (got.float() - want).abs()
+    tol = 2.0 ** -7 * want.abs() + 2e-2
+    assert bool((err <= tol).all()), float((err - tol).max())
+    rel = float((got.float() - want).norm() / want.norm().clamp_min(1e-6))
+    assert rel <= 8e-3, rel
+
+
+@pytest.mark.gpu
+def test_group_norm_nhwc_rejects_bad_inputs():
+    from confild_b200.latent_sampler import group_norm_nhwc
+
+    x = torch.zeros(2, 20, 4, 4, device="cuda", dtype=torch.bfloat16)  # 20 channels: not a multiple of 8
+    w = torch.ones(20, device="cuda")
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        group_norm_nhwc(x, w, w, 4)
+    with pytest.raises(ValueError):
+        group_norm_nhwc(x.float(), w, w, 4)
+    x = torch.zeros(2, 32, 4, 4, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        group_norm_nhwc(x, torch.ones(32, device="cuda"), torch.ones(31, device="cuda"), 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny", "mid"])
+def test_forward_inference_matches_autocast_and_fp32(name):
+    """LatentUNet.forward_inference (bf16 channels-last, fused GroupNorm+SiLU+embedding add, linear-form attention)
+    against the same module's forward in fp32 and under bf16 autocast: it must be as close to fp32 as autocast is."""
+    cfg = LAYOUTS["tiny"]["config"] if name == "tiny" else dict(
+        image_size=64, num_channels=64, num_res_blocks=2, num_heads=4, num_head_channels=32,
+        attention_resolutions="32,16,8")
+    m = LatentUNet(**cfg).eval()
+    m.load_state_dict(seeded_weights(m.state_dict()))
+    m = m.cuda()
+    S = 32 if name == "tiny" else 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(2, 1, S, S, device="cuda", generator=g)
+    t = torch.tensor([17, 930], device="cuda")
+    with torch.no_grad():
+        want = m(x, t)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            auto = m(x.contiguous(memory_format=torch.channels_last), t).float()
+        got = m.forward_inference(x, t)
+    assert got.shape == want.shape and got.dtype == x.dtype and got.is_contiguous()
+    e_auto = float((auto - want).norm() / want.norm())
+    e_fast = float((got - want).norm() / want.norm())
+    print(f"{name}: rel_l2 vs fp32: autocast {e_auto:.3e}, forward_inference {e_fast:.3e}")
+    assert e_fast <= max(5e-2, 1.5 * e_auto)
+    # stale-weight protection: prepare_inference() picks up new weights
+    with torch.no_grad():
+        for p in m.parameters():
+            p.mul_(0.5)
+        m.prepare_inference()
+        got2 = m.forward_inference(x, t)
+        want2 = m(x, t)
+    assert float((got2 - want2).norm() / want2.norm()) <= 5e-2
+    # the graph-captured sampler with and without the fast path gives finite, similar-magnitude latents
+    z = sample_latents(m, (2, 1, S, S), steps=5, device="cuda")
+    z0 = sample_latents(m, (2, 1, S, S), steps=5, device="cuda", fast_unet=False)
+    assert torch.isfinite(z).all() and torch.isfinite(z0).all() and float(z.abs().max()) < 50
+
+
+@pytest.mark.gpu
 def test_generate_fields_end_to_end_small():
     """Sampler -> latent de-normalisation -> batched CNF decode (scripts/inference.py:55-79 as one call)."""
     from oracle import cnf_oracle as O
