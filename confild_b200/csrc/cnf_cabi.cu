@@ -278,9 +278,10 @@ int cnf_film_shift(const cnf_dims* dims, const void* d_packed, const float* d_la
   const uint8_t* packed = static_cast<const uint8_t*>(d_packed);
   const int N = (dims->nl + 1) * dims->H;
   dim3 grid((N + 63) / 64, (unsigned)((T + 63) / 64));
-  cnf::simt_gemm_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (grid.y > 65535) return fail(CNF_ERR_UNSUPPORTED, "T=%lld exceeds the grid limit", (long long)T);
+  cnf::simt_gemm_kernel<true, false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_latents, reinterpret_cast<const float*>(packed + lay.v_cat),
-      reinterpret_cast<const float*>(packed + lay.b_shift), d_shift, T, N, dims->L);
+      reinterpret_cast<const float*>(packed + lay.b_shift), d_shift, T, N, dims->L, dims->L, nullptr);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;
 }
@@ -295,10 +296,20 @@ int cnf_film_shift_backward_scaled(const cnf_dims* dims, const void* d_packed, c
   const int K = (dims->nl + 1) * dims->H;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CNF_CUDA(cudaMemsetAsync(d_glatents, 0, (size_t)T * dims->L * sizeof(float), st));
-  if (T > 2147483647LL) return fail(CNF_ERR_UNSUPPORTED, "T=%lld exceeds the grid limit", (long long)T);
-  dim3 grid((unsigned)T, (unsigned)((K + cnf::kShiftBwdChunk - 1) / cnf::kShiftBwdChunk));
-  cnf::film_shift_backward_kernel<<<grid, 128, 0, st>>>(d_gshift, reinterpret_cast<const float*>(packed + lay.v_cat),
-                                                       d_glatents, K, dims->L, d_scale);
+  // glat (T, L) = gshift (T, K) . V (K, L): few output tiles, long reduction -> split K until ~2 waves of CTAs exist
+  const int64_t tiles = ((T + 63) / 64) * ((dims->L + 63) / 64);
+  if ((T + 63) / 64 > 65535) return fail(CNF_ERR_UNSUPPORTED, "T=%lld exceeds the grid limit", (long long)T);
+  cnf::host::DeviceInfo di;
+  if (int rc = cnf::host::device_info(&di)) return rc;
+  int64_t splits = (2 * (int64_t)di.sms + tiles - 1) / tiles;
+  const int64_t max_splits = (K + 63) / 64;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int kc = (int)(((K + splits - 1) / splits + 15) / 16 * 16);
+  splits = (K + kc - 1) / kc;
+  dim3 grid((unsigned)((dims->L + 63) / 64), (unsigned)((T + 63) / 64), (unsigned)splits);
+  cnf::simt_gemm_kernel<false, true><<<grid, 256, 0, st>>>(d_gshift, reinterpret_cast<const float*>(packed + lay.v_cat),
+                                                          nullptr, d_glatents, T, dims->L, K, kc, d_scale);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;
 }

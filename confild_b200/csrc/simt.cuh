@@ -9,49 +9,76 @@
 namespace cnf {
 
 // ------------------------------------------------------------------------------------------
-// C[m][n] = sum_k A[m][k] * Bop[k][n] (+ bias[n]);  B_NK: B stored [N][K] (row-dot), else [K][N].
-// 64x64 output tile per 256-thread block, 4x4 outputs per thread, K staged 16 at a time.
-template <bool B_NK>
+// C[m][n] (+)= scale * sum_k A[m][k] * Bop[k][n] (+ bias[n]);  B_NK: B stored [N][K] (row-dot), else [K][N].
+// 64x64 output tile per 256-thread block, 4x4 outputs per thread, K staged 16 at a time through double-buffered shared
+// memory (global loads of step i+1 in flight under the FMAs of step i; operands read back as 16-byte vectors).
+// SPLITK: blockIdx.z owns the K range [z*kc, (z+1)*kc) and adds its partial tile to a pre-zeroed C with atomics -- the
+// DPS shapes (K4: M = 64..384 frames, N = L <= 384, K = (nl+1)H up to 6,144) have only a handful of output tiles.
+template <bool B_NK, bool SPLITK>
 __global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                         const float* __restrict__ bias, float* __restrict__ C,
-                                                        int64_t M, int N, int K) {
-  __shared__ float As[16][65];
-  __shared__ float Bs[16][65];
+                                                        int64_t M, int N, int K, int kc,
+                                                        const float* __restrict__ scale) {
+  constexpr int LD = 68;  // row stride in floats: 16-byte aligned rows, conflict-free transposed stores
+  __shared__ __align__(16) float As[2][16][LD];
+  __shared__ __align__(16) float Bs[2][16][LD];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   const int64_t m0 = (int64_t)blockIdx.y * 64;
   const int n0 = blockIdx.x * 64;
+  const int k_begin = SPLITK ? (int)blockIdx.z * kc : 0;
+  const int k_end = SPLITK ? min(K, k_begin + kc) : K;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = tid + i * 256;
       {
         const int m = e / 16, k = e % 16;
-        As[k][m] = (m0 + m < M && k0 + k < K) ? A[(m0 + m) * K + k0 + k] : 0.f;
+        ra[i] = (m0 + m < M && k0 + k < k_end) ? __ldg(A + (m0 + m) * K + k0 + k) : 0.f;
       }
       if (B_NK) {
         const int n = e / 16, k = e % 16;
-        Bs[k][n] = (n0 + n < N && k0 + k < K) ? B[(size_t)(n0 + n) * K + k0 + k] : 0.f;
+        rb[i] = (n0 + n < N && k0 + k < k_end) ? __ldg(B + (size_t)(n0 + n) * K + k0 + k) : 0.f;
       } else {
         const int k = e / 64, n = e % 64;
-        Bs[k][n] = (n0 + n < N && k0 + k < K) ? B[(size_t)(k0 + k) * N + n0 + n] : 0.f;
+        rb[i] = (n0 + n < N && k0 + k < k_end) ? __ldg(B + (size_t)(k0 + k) * N + n0 + n) : 0.f;
       }
     }
-    __syncthreads();
+  };
+  auto stage = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      As[buf][e % 16][e / 16] = ra[i];
+      if (B_NK) Bs[buf][e % 16][e / 16] = rb[i];
+      else Bs[buf][e / 64][e % 64] = rb[i];
+    }
+  };
+  if (k_begin < k_end) {
+    fetch(k_begin);
+    stage(0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = k_begin; k0 < k_end; k0 += 16, buf ^= 1) {
+    const bool more = k0 + 16 < k_end;
+    if (more) fetch(k0 + 16);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+    if (more) stage(buf ^ 1);  // the other buffer was last read before the previous barrier
     __syncthreads();
   }
+  const float sc = scale != nullptr ? __ldg(scale) : 1.f;
+  const bool add_bias = bias != nullptr && (!SPLITK || blockIdx.z == 0);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int64_t m = m0 + ty * 4 + i;
@@ -59,31 +86,11 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < N) C[m * N + n] = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (n >= N) continue;
+      const float v = acc[i][j] * sc + (add_bias ? bias[n] : 0.f);
+      if (SPLITK) atomicAdd(C + m * N + n, v);
+      else C[m * N + n] = v;
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// glat[t][j] += sum_{i in this block's K chunk} gshift[t][i] * V[i][j]   (K = (nl+1)*H, V row-major [K][L]).
-// The DPS shapes have few frames (T = 64..384) and a long reduction (K = 1408..6144): a (frame, K-chunk) grid with
-// split-K atomics keeps every SM busy where a 64x64-tile GEMM would run on one or two blocks.  glat is pre-zeroed.
-constexpr int kShiftBwdChunk = 128;
-// `scale` (optional, device): every output is multiplied by *scale -- the 1/||r|| of the fused DPS loss.
-__global__ void __launch_bounds__(128) film_shift_backward_kernel(const float* __restrict__ gshift,
-                                                                  const float* __restrict__ V, float* __restrict__ glat,
-                                                                  int K, int L, const float* __restrict__ scale) {
-  __shared__ float gs[kShiftBwdChunk];
-  const int64_t t = blockIdx.x;
-  const int i0 = blockIdx.y * kShiftBwdChunk;
-  const int n = min(kShiftBwdChunk, K - i0);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) gs[i] = gshift[t * K + i0 + i];
-  __syncthreads();
-  for (int j = threadIdx.x; j < L; j += blockDim.x) {
-    float acc = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < n; ++i) acc = fmaf(gs[i], __ldg(V + (size_t)(i0 + i) * L + j), acc);
-    atomicAdd(glat + t * L + j, scale ? acc * __ldg(scale) : acc);
   }
 }
 
