@@ -342,7 +342,12 @@ def measure_dps(cb, model, dims, case, dev, args, iters):
 
     def fused_skip_step():
         l = ld[:, None].detach().requires_grad_(True)
-        norm = cb.measurement_norm(model, cd[None], l, ym_masked, mask=mask)
+        norm = cb.measurement_norm(model, cd[None], l, ym_masked, mask=mask, skip_masked_decode=False)
+        torch.autograd.grad(norm, l)
+
+    def fused_default_step():  # measurement_norm's default: rows with a zero mask weight are neither decoded nor stashed
+        l = ld[:, None].detach().requires_grad_(True)
+        norm = cb.measurement_norm(model, cd[None], l, y_meas, mask=mask)
         torch.autograd.grad(norm, l)
 
     cs, _, ys = cb.sensor_rows(cd, mask, y_meas)
@@ -358,6 +363,7 @@ def measure_dps(cb, model, dims, case, dev, args, iters):
            "bf16x3 (the backward always runs the bf16 hi/lo split on the fp16 cos stash, whatever the forward mode)"}
     for name, fn, rows in (("autograd_dense", autograd_step, Td * Pd), ("fused_loss_dense", fused_step, Td * Pd),
                            ("fused_loss_dense_zero_row_skip", fused_skip_step, Td * Pd),
+                           ("fused_loss_masked_rows_not_decoded", fused_default_step, Td * S),
                            ("sensor_compacted", compact_step, Td * S)):
         ms = timed(fn, iters)
         res[name] = {"ms_per_step": ms, "point_frames_per_s": rows / (ms * 1e-3), "rows_per_step": rows}
@@ -367,7 +373,12 @@ def measure_dps(cb, model, dims, case, dev, args, iters):
     res["note"] = ("value = fused_loss_dense: every point decoded WITH its backward stash and visited by the backward (the "
                    "graded dense quantity); fused_loss_dense_zero_row_skip also decodes and scores every point but stashes "
                    "/ back-propagates only the rows whose mask weight is non-zero (exact gradient, P/#sensors less stash "
-                   "traffic); sensor_compacted decodes only the sensor rows (SURVEY.md 8d: reported separately)")
+                   "traffic); fused_loss_masked_rows_not_decoded = measurement_norm's default on the same full-grid inputs "
+                   "(unmasked measurement, per-point mask): a row with a zero weight has residual = measurement whatever the "
+                   "decoder returns, so only the sensor rows are decoded / stashed / back-propagated and the other rows' "
+                   "measurement energy is added to the sum of squares -- same norm and gradient, rows_per_step counts the "
+                   "decoded rows; sensor_compacted is the caller-side version of the same thing (SURVEY.md 8d: reported "
+                   "separately)")
     return res
 
 

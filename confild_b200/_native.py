@@ -37,7 +37,8 @@ class CnfSensorLoss(ctypes.Structure):
     """``cnf_sensor_loss`` of include/confild_cnf.h."""
     _fields_ = [("d_y_meas", ctypes.c_void_p), ("d_mask", ctypes.c_void_p), ("mask_kind", ctypes.c_int32),
                 ("y_scale", ctypes.c_float * 4), ("y_offset", ctypes.c_float * 4),
-                ("d_gy", ctypes.c_void_p), ("d_partials", ctypes.c_void_p), ("d_norm", ctypes.c_void_p)]
+                ("d_gy", ctypes.c_void_p), ("d_partials", ctypes.c_void_p), ("d_norm", ctypes.c_void_p),
+                ("d_extra_sq", ctypes.c_void_p)]
 
 
 _lib: Optional[ctypes.CDLL] = None

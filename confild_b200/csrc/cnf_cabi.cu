@@ -377,7 +377,7 @@ int cnf_forward_loss(const cnf_dims* dims, const void* d_packed, int precision, 
   if (int rc = forward_impl(dims, d_packed, precision, d_coords, coord_frame_stride, d_shift, outs, T, P, d_stash,
                             stash_bytes, &la, stream))
     return rc;
-  cnf::loss_finalize_kernel<<<1, 1024, 0, st>>>(loss->d_partials, CNF_LOSS_PARTIALS, loss->d_norm);
+  cnf::loss_finalize_kernel<<<1, 1024, 0, st>>>(loss->d_partials, CNF_LOSS_PARTIALS, loss->d_norm, loss->d_extra_sq);
   CNF_CUDA(cudaGetLastError());
   return CNF_OK;
 }

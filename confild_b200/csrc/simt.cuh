@@ -96,8 +96,11 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const float* __restrict_
 
 // Fused-loss finalize: ||r|| = sqrt(sum of the head warps' partial sums of r^2), summed in double in a fixed order.
 // norm[0] = ||r||, norm[1] = 1/||r|| (0 when ||r|| == 0: the subgradient torch.linalg.norm's backward uses).
+// `extra_sq` (optional, device): a term added to the sum of squares -- the measurement energy of rows that were not
+// decoded because their mask weight is zero (r = y_meas there, whatever the network says).
 __global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __restrict__ partials, int n,
-                                                             float* __restrict__ norm) {
+                                                             float* __restrict__ norm,
+                                                             const float* __restrict__ extra_sq) {
   __shared__ double red[32];
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partials[i];
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(const float* __rest
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if (threadIdx.x == 0) {
+      if (extra_sq != nullptr) v += fmax((double)*extra_sq, 0.0);
       const double nrm = sqrt(v);
       norm[0] = (float)nrm;
       norm[1] = nrm > 0.0 ? (float)(1.0 / nrm) : 0.f;

@@ -19,6 +19,7 @@ coordinates / measurements of the rows the mask keeps, so that decode + backward
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -38,28 +39,43 @@ def _mask_kind(mask: torch.Tensor, T: int, P: int, cout: int) -> Tuple[torch.Ten
     return m.expand(torch.broadcast_shapes(tuple(m.shape), (T, P, cout))).reshape(T, P, cout).contiguous(), 3
 
 
-#: per-point masks seen so far -> indices of their non-zero rows (a DPS loop passes the same mask tensor every step, so
-#: the one host synchronisation that `nonzero` costs is paid once); keyed on (data_ptr, version, numel, device)
-_ROW_CACHE: dict = {}
 #: skip the backward stash for masked-out rows when at most this fraction of the points carries a non-zero weight
 ZERO_ROW_SKIP_MAX_FRACTION = 0.5
 
+# A guided-sampling loop calls measurement_norm a thousand times with the SAME measurement, mask and coordinate tensors:
+# everything derived from them alone (canonical layouts, the indices of the kept rows -- whose `nonzero` costs a host
+# synchronisation --, the gathered rows, the dropped rows' measurement energy) is cached.  Entries are keyed on the
+# identity of the caller's tensor objects and validated by weak reference and in-place version counter, so a recycled
+# address or an in-place update can never produce a stale hit.
+_CACHE: dict = {}
+_CACHE_MAX = 64
+
+
+def _cached(name: str, tensors, extra: tuple, make):
+    key = (name,) + tuple(id(t) for t in tensors) + extra
+    ent = _CACHE.get(key)
+    if ent is not None:
+        refs, versions, val = ent
+        if all(r() is t and t._version == v for r, v, t in zip(refs, versions, tensors)):
+            return val
+        del _CACHE[key]
+    val = make()
+    if len(_CACHE) >= _CACHE_MAX:
+        _CACHE.clear()
+    _CACHE[key] = ([weakref.ref(t) for t in tensors], [t._version for t in tensors], val)
+    return val
+
 
 def _kept_rows(mask1d: torch.Tensor) -> torch.Tensor:
-    key = (mask1d.data_ptr(), mask1d._version, mask1d.numel(), str(mask1d.device))
-    idx = _ROW_CACHE.get(key)
-    if idx is None:
-        if len(_ROW_CACHE) > 64:
-            _ROW_CACHE.clear()
-        idx = torch.nonzero(mask1d != 0, as_tuple=False).reshape(-1)
-        _ROW_CACHE[key] = idx
-    return idx
+    return torch.nonzero(mask1d != 0, as_tuple=False).reshape(-1)
 
 
 class _MeasurementNormFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, lat2d, coords_c, frame_stride, module, y_meas, mask, mask_kind, ya, yb, want_grad, want_field,
-                zero_row_skip=True):
+                kept=None, rows=None):
+        # kept: indices of the rows with a non-zero per-point weight (zero-row skip), or None;
+        # rows: (coords_k, meas_k, mask_k, extra_sq) when only the kept rows are to be decoded at all, else None
         lib = _native.load()
         d = module._cdims()
         cin, L, H, nl, cout = module._dims_tuple
@@ -68,21 +84,21 @@ class _MeasurementNormFunction(torch.autograd.Function):
         dev = lat2d.device
         packed = module._ensure_packed()
         shift = torch.empty((T, (nl + 1) * H), dtype=torch.float32, device=dev)
-        field = torch.empty((T, P, cout), dtype=torch.float32, device=dev) if (
-            want_field or prec == _native.PREC_FP32) else None
-        gy = torch.empty((T, P, cout), dtype=torch.float32, device=dev)
         partials = torch.empty(_native.LOSS_PARTIALS, dtype=torch.float32, device=dev)
         norm = torch.empty(2, dtype=torch.float32, device=dev)
         # Rows whose per-point weight is zero have an identically zero seed: with a sparse per-point mask the dense pass
         # below runs WITHOUT the backward stash (every point is still decoded and enters the norm) and only the kept
         # rows are decoded a second time with the stash for the backward -- the stash traffic (2.8 KB / 12 KB per
         # point-frame at case1 / case4) shrinks by P / #kept while the gradient stays exact.
-        kept = None
-        if (want_grad and zero_row_skip and mask is not None and mask_kind == 1 and frame_stride == 0
-                and prec != _native.PREC_FP32):
-            idx = _kept_rows(mask)
-            if 0 < idx.numel() <= ZERO_ROW_SKIP_MAX_FRACTION * P:
-                kept = idx
+        if rows is not None:
+            # Nobody looks at the decoded field, and a row with a zero weight has r = y_meas whatever the decoder
+            # returns: decode (with the stash), score and back-propagate the kept rows only and add the dropped rows'
+            # measurement energy to the sum of squares (cnf_sensor_loss.d_extra_sq) -- same norm, same gradient.
+            return _MeasurementNormFunction._kept_rows_only(ctx, lib, d, module, prec, packed, lat2d, shift, rows, ya, yb,
+                                                            partials, norm)
+        field = torch.empty((T, P, cout), dtype=torch.float32, device=dev) if (
+            want_field or prec == _native.PREC_FP32) else None
+        gy = torch.empty((T, P, cout), dtype=torch.float32, device=dev)
         stash, stash_n = None, 0
         if want_grad and kept is None:
             stash_n = _native.stash_bytes(d, prec, T, P)
@@ -131,15 +147,48 @@ class _MeasurementNormFunction(torch.autograd.Function):
         return out_norm, torch.empty(0, device=dev)
 
     @staticmethod
+    def _kept_rows_only(ctx, lib, d, module, prec, packed, lat2d, shift, rows, ya, yb, partials, norm):
+        cin, L, H, nl, cout = module._dims_tuple
+        coords_k, meas_k, mask_k, extra = rows
+        T, dev, Pk = lat2d.shape[0], lat2d.device, int(coords_k.shape[0])
+        gy = torch.empty((T, Pk, cout), dtype=torch.float32, device=dev)
+        stash_n = _native.stash_bytes(d, prec, T, Pk)
+        stash = torch.empty(stash_n, dtype=torch.uint8, device=dev)
+        loss = _native.CnfSensorLoss()
+        loss.d_y_meas, loss.d_mask, loss.mask_kind = meas_k.data_ptr(), mask_k.data_ptr(), 1
+        for o in range(4):
+            loss.y_scale[o] = float(ya[o]) if o < cout else 1.0
+            loss.y_offset[o] = float(yb[o]) if o < cout else 0.0
+        loss.d_gy, loss.d_partials, loss.d_norm = gy.data_ptr(), partials.data_ptr(), norm.data_ptr()
+        loss.d_extra_sq = extra.data_ptr()
+        gshift = torch.empty((T, (nl + 1) * H), dtype=torch.float32, device=dev)
+        glat = torch.empty((T, L), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _native.check(lib.cnf_film_shift(d, packed.data_ptr(), lat2d.data_ptr(), T, shift.data_ptr(), stream),
+                          "cnf_film_shift")
+            _native.check(lib.cnf_forward_loss(d, packed.data_ptr(), prec, coords_k.data_ptr(), 0, shift.data_ptr(), None,
+                                               T, Pk, stash.data_ptr(), stash_n, ctypes.byref(loss), stream),
+                          "cnf_forward_loss")
+            _native.check(lib.cnf_backward(d, packed.data_ptr(), prec, gy.data_ptr(), stash.data_ptr(), stash_n,
+                                           gshift.data_ptr(), T, Pk, stream), "cnf_backward")
+            _native.check(lib.cnf_film_shift_backward_scaled(d, packed.data_ptr(), gshift.data_ptr(), T,
+                                                             norm[1:].data_ptr(), glat.data_ptr(), stream),
+                          "cnf_film_shift_backward_scaled")
+        ctx.glat = glat
+        return norm[0], torch.empty(0, device=dev)
+
+    @staticmethod
     def backward(ctx, gnorm, _gfield):
         if ctx.glat is None:
             raise RuntimeError("measurement_norm was evaluated without gradient tracking of the latents")
-        return ctx.glat * gnorm, None, None, None, None, None, None, None, None, None, None, None
+        return ctx.glat * gnorm, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 def measurement_norm(model: SIRENAutodecoder_film, coords: torch.Tensor, latents: torch.Tensor,
                      measurement: torch.Tensor, mask: Optional[torch.Tensor] = None, y_normalizer=None,
-                     mask_measurement: bool = False, return_field: bool = False, zero_row_skip: bool = True):
+                     mask_measurement: bool = False, return_field: bool = False, zero_row_skip: bool = True,
+                     skip_masked_decode: bool = True):
     """``torch.linalg.norm(measurement - mask * y_normalizer.denormalize(model(coords, latents)))`` as one fused
     CUDA pass, differentiable with respect to ``latents``.
 
@@ -149,7 +198,11 @@ def measurement_norm(model: SIRENAutodecoder_film, coords: torch.Tensor, latents
     measurement first.  ``y_normalizer`` is the reference's ``Normalizer_ts`` (any of its affine methods) or ``None``.
     With ``return_field=True`` returns ``(norm, y_phys)`` where ``y_phys`` is the decoded (denormalised, unmasked) field.
     ``zero_row_skip`` (default on): with a sparse per-point mask the backward only visits the rows whose weight is
-    non-zero (their seed is identically zero otherwise); every point is still decoded and enters the norm.
+    non-zero (their seed is identically zero otherwise).  ``skip_masked_decode`` (default on, effective together with
+    ``zero_row_skip`` when the field is not requested): those rows are not decoded either -- their residual is the
+    measurement itself, so only its energy enters the norm; with ``skip_masked_decode=False`` (or ``return_field=True``)
+    every point is decoded and scored by the kernel.  Norm and gradient are the same in all three modes up to fp32
+    summation order.
     """
     dev = model._check_inputs(coords, latents)
     grad_on = model._check_grad_mode(coords)
@@ -162,17 +215,41 @@ def measurement_norm(model: SIRENAutodecoder_film, coords: torch.Tensor, latents
         ya, yb = ya.tolist(), yb.tolist()
     else:
         ya, yb = [1.0] * cout, [0.0] * cout
-    y_meas = measurement.to(device=dev, dtype=torch.float32)
+    shape_key = (T, P, cout, tuple(out_lead), str(dev))
     mk, kind = (None, 0)
     if mask is not None:
-        mk, kind = _mask_kind(mask.to(dev), T, P, cout)
-        if mask_measurement:
-            mfull = mk.reshape((1, P, 1) if kind == 1 else (1, P, cout) if kind == 2 else (T, P, cout))
-            y_meas = y_meas.expand(out_lead + (cout,)).reshape(T, P, cout) * mfull
-    y_meas = y_meas.expand(out_lead + (cout,)).reshape(T, P, cout).contiguous()
+        mk, kind = _cached("mask", (mask,), shape_key, lambda: _mask_kind(mask.to(dev), T, P, cout))
+
+    def prepare_measurement():
+        y = measurement.to(device=dev, dtype=torch.float32).expand(out_lead + (cout,)).reshape(T, P, cout)
+        if mask is not None and mask_measurement:
+            y = y * mk.reshape((1, P, 1) if kind == 1 else (1, P, cout) if kind == 2 else (T, P, cout))
+        return y.contiguous()
+
+    y_meas = _cached("meas", (measurement,) + ((mask,) if mask is not None else ()),
+                     shape_key + (bool(mask_measurement),), prepare_measurement)
     want_grad = grad_on and lat2d.requires_grad
+    # zero-row skip: the rows a sparse per-point mask keeps (frame-shared coordinates, tensor-core precisions)
+    kept, rows = None, None
+    if (want_grad and zero_row_skip and kind == 1 and stride == 0 and model._precision_code() != _native.PREC_FP32):
+        idx = _cached("kept", (mask,), shape_key, lambda: _kept_rows(mk))
+        if 0 < idx.numel() <= ZERO_ROW_SKIP_MAX_FRACTION * P:
+            kept = idx
+    if kept is not None and skip_masked_decode and not return_field:
+        coords_k = _cached("coords_k", (coords, mask), shape_key, lambda: coords_c.index_select(0, kept).contiguous())
+        mask_k = _cached("mask_k", (mask,), shape_key, lambda: mk.index_select(0, kept).contiguous())
+
+        def gather_measurement():
+            meas_k = y_meas.index_select(1, kept).contiguous()
+            # energy of the dropped rows = total - kept, in double (zero when the measurement is already masked)
+            extra = (torch.linalg.vector_norm(y_meas, dtype=torch.float64).square()
+                     - torch.linalg.vector_norm(meas_k, dtype=torch.float64).square())
+            return meas_k, extra.clamp_min(0).to(torch.float32).reshape(1)
+
+        meas_k, extra = _cached("meas_k", (measurement, mask), shape_key + (bool(mask_measurement),), gather_measurement)
+        rows = (coords_k, meas_k, mask_k, extra)
     norm, field = _MeasurementNormFunction.apply(lat2d, coords_c, stride, model, y_meas, mk, kind, ya, yb, want_grad,
-                                                 return_field, zero_row_skip)
+                                                 return_field, kept, rows)
     if return_field:
         ya_t = torch.tensor(ya, device=dev)
         yb_t = torch.tensor(yb, device=dev)

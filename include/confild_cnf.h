@@ -168,6 +168,9 @@ typedef struct cnf_sensor_loss {
   float* d_gy;           /* (T,P,cout) out                                                                */
   float* d_partials;     /* CNF_LOSS_PARTIALS floats of scratch (per-warp partial sums of r^2)            */
   float* d_norm;         /* 2 floats out                                                                  */
+  const float* d_extra_sq; /* NULL, or one device float added to sum r^2 before the square root: the energy
+                            * sum y_meas^2 of rows the caller did not pass because their mask weight is zero
+                            * (r = y_meas there whatever the decoder returns)                             */
 } cnf_sensor_loss;
 int cnf_forward_loss(const cnf_dims* dims, const void* d_packed, int precision, const float* d_coords,
                      int64_t coord_frame_stride, const float* d_shift, float* d_out, int64_t T, int64_t P,

@@ -746,6 +746,52 @@ def test_measurement_norm_no_grad_and_zero_residual():
 
 
 @pytest.mark.gpu
+def test_measurement_norm_caches_follow_in_place_updates_and_new_tensors():
+    """The per-loop caches of dps.py (canonical measurement / mask, kept rows, gathered rows) are keyed on tensor identity
+    and version: an in-place update or a fresh tensor must never be answered from a stale entry."""
+    dims = O.CASE_SHAPES["case1"]
+    sd = O.init_params(*dims, seed=0)
+    m = make_model(dims, sd, "f16f8")
+    m.disable_gradient()
+    T, P = 4, 2000
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    c = coords.cuda()
+    mask = torch.zeros(P, device="cuda")
+    mask[:150] = 1.0
+    meas = (torch.randn(T, P, dims[2], generator=torch.Generator().manual_seed(1)) * 0.3).cuda()
+
+    def run(ms, mk, **kw):
+        l = lat.cuda()[:, None].requires_grad_(True)
+        n = cb.measurement_norm(m, c[None], l, ms, mask=mk, **kw)
+        (g,) = torch.autograd.grad(n, l)
+        return float(n), g
+
+    def ref(ms, mk):
+        return run(ms.clone(), mk.clone(), zero_row_skip=False)  # fresh objects, dense path: never cached
+
+    n0, g0 = run(meas, mask)
+    n0b, g0b = run(meas, mask)  # served from the caches
+    assert n0 == n0b and O.rel_l2(g0, g0b) <= 1e-5  # (the backward accumulates with atomics: not bitwise)
+    r0, gr0 = ref(meas, mask)
+    assert abs(n0 - r0) <= 2e-6 * r0 and O.rel_l2(g0, gr0) <= 1e-4
+    meas.mul_(2.0)  # in-place: same object, new version
+    n1, g1 = run(meas, mask)
+    r1, gr1 = ref(meas, mask)
+    assert abs(n1 - r1) <= 2e-6 * r1 and O.rel_l2(g1, gr1) <= 1e-4 and n1 > 1.5 * n0
+    mask[150:300] = 1.0  # more sensors, in place
+    n2, g2 = run(meas, mask)
+    r2, gr2 = ref(meas, mask)
+    assert abs(n2 - r2) <= 2e-6 * r2 and O.rel_l2(g2, gr2) <= 1e-4 and O.rel_l2(g2, g1) > 1e-2
+    for k in range(3):  # fresh tensors every call (addresses may be recycled by the allocator)
+        ms = meas * (1.0 + k)
+        mk = mask.clone()
+        n3, g3 = run(ms, mk)
+        r3, gr3 = ref(ms, mk)
+        assert abs(n3 - r3) <= 2e-6 * r3 and O.rel_l2(g3, gr3) <= 1e-4
+        del ms, mk
+
+
+@pytest.mark.gpu
 def test_sensor_rows_compaction_matches_dense_gradient():
     """f3: dense-grid operator with a binary per-point mask: decoding only the kept rows gives the same latent
     gradient (and the same norm once the masked-out measurement energy is added back)."""
@@ -764,8 +810,22 @@ def test_sensor_rows_compaction_matches_dense_gradient():
     (g_dense,) = torch.autograd.grad(n_dense, l1)
     l3 = lat.cuda()[:, None].requires_grad_(True)
     n_full = cb.measurement_norm(m, c[None], l3, y_meas, mask=mk, mask_measurement=True, zero_row_skip=False)
-    (g_full,) = torch.autograd.grad(n_full, l3)  # dense stash for every row vs the zero-row skip (default) above
-    assert float(n_full) == float(n_dense) and O.rel_l2(g_dense, g_full) <= 1e-4
+    (g_full,) = torch.autograd.grad(n_full, l3)  # dense stash for every row
+    l4 = lat.cuda()[:, None].requires_grad_(True)
+    n_skip = cb.measurement_norm(m, c[None], l4, y_meas, mask=mk, mask_measurement=True, skip_masked_decode=False)
+    (g_skip,) = torch.autograd.grad(n_skip, l4)  # every row decoded and scored, only the kept rows stashed
+    assert float(n_full) == float(n_skip) and O.rel_l2(g_skip, g_full) <= 1e-4
+    # default: the masked-out rows are not decoded at all (their measurement energy is added to the sum of squares)
+    assert abs(float(n_dense) - float(n_full)) <= 2e-6 * float(n_full) and O.rel_l2(g_dense, g_full) <= 1e-4
+    # ... also when the measurement is NOT masked (the dropped rows then carry most of the norm)
+    l5 = lat.cuda()[:, None].requires_grad_(True)
+    n_a = cb.measurement_norm(m, c[None], l5, y_meas, mask=mk)
+    (g_a,) = torch.autograd.grad(n_a, l5)
+    l6 = lat.cuda()[:, None].requires_grad_(True)
+    n_b = cb.measurement_norm(m, c[None], l6, y_meas, mask=mk, zero_row_skip=False)
+    (g_b,) = torch.autograd.grad(n_b, l6)
+    assert float(n_a) > 3 * float(n_full)
+    assert abs(float(n_a) - float(n_b)) <= 2e-6 * float(n_b) and O.rel_l2(g_a, g_b) <= 1e-4
     cs, idx, ys = cb.sensor_rows(c, mk, y_meas)
     assert cs.shape == (300, dims[0]) and ys.shape == (T, 300, dims[2])
     l2 = lat.cuda()[:, None].requires_grad_(True)

@@ -1,12 +1,10 @@
-"""A few DPS steps of BASELINE config 4 (profiling target):
-    python tests/tools/dps_once.py case1 [skip|dense]
-64 latents x 16,384 points, 1,000 random sensors, fused measurement norm + gradient; `dense` stashes every row,
-`skip` (default policy) only the sensor rows.  Prints the CUDA-event time per step."""
+"""Kernel table (torch profiler) of the DPS step of BASELINE config 4: python tests/tools/dps_profile.py case1 [skip|dense]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import confild_b200 as cb
 from oracle import cnf_oracle as O
+from torch.profiler import profile, ProfilerActivity
 case = sys.argv[1] if len(sys.argv) > 1 else "case1"
 mode = sys.argv[2] if len(sys.argv) > 2 else "skip"
 dims = O.CASE_SHAPES[case]; sd = O.init_params(*dims, seed=0)
@@ -20,15 +18,9 @@ def step():
     l = l0[:, None].detach().requires_grad_(True)
     n = cb.measurement_norm(m, c[None], l, ym, mask=mask, zero_row_skip=(mode == "skip"))
     return torch.autograd.grad(n, l)[0]
-for _ in range(3): step()
+for _ in range(5): step()
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(5): g = step()
-e1.record(); torch.cuda.synchronize()
-import time
-ts = []
-for _ in range(12):
-    torch.cuda.synchronize(); t0 = time.perf_counter(); step(); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
-print("wall ms per step:", " ".join(f"{t:.2f}" for t in ts))
-print(f"{case} DPS step ({mode}, {m.resolved_precision}): {e0.elapsed_time(e1) / 5:.3f} ms; |g| = {float(g.norm()):.4e}")
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(5): step()
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=20, max_name_column_width=70))
