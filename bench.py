@@ -350,6 +350,12 @@ def measure_dps(cb, model, dims, case, dev, args, iters):
         norm = cb.measurement_norm(model, cd[None], l, y_meas, mask=mask)
         torch.autograd.grad(norm, l)
 
+    graphed = cb.GraphedMeasurementNorm(model, cd[None], ld[:, None], y_meas, mask=mask)
+
+    def fused_graph_step():  # the same step captured once in a CUDA graph (GraphedMeasurementNorm) and replayed
+        l = ld[:, None].detach().requires_grad_(True)
+        torch.autograd.grad(graphed(l), l)
+
     cs, _, ys = cb.sensor_rows(cd, mask, y_meas)
 
     def compact_step():
@@ -364,6 +370,7 @@ def measure_dps(cb, model, dims, case, dev, args, iters):
     for name, fn, rows in (("autograd_dense", autograd_step, Td * Pd), ("fused_loss_dense", fused_step, Td * Pd),
                            ("fused_loss_dense_zero_row_skip", fused_skip_step, Td * Pd),
                            ("fused_loss_masked_rows_not_decoded", fused_default_step, Td * S),
+                           ("fused_loss_masked_rows_not_decoded_cuda_graph", fused_graph_step, Td * S),
                            ("sensor_compacted", compact_step, Td * S)):
         ms = timed(fn, iters)
         res[name] = {"ms_per_step": ms, "point_frames_per_s": rows / (ms * 1e-3), "rows_per_step": rows}
@@ -424,9 +431,16 @@ def measure_extra(model, coords, lat, dev, args):
         l = ln[:, None].detach().requires_grad_(True)
         torch.autograd.grad(cb.measurement_norm(m4, cn[None], l, ymn), l)
 
+    nb_graphed_fn = cb.GraphedMeasurementNorm(m4, cn[None], ln[:, None], ymn)
+
+    def nb_graphed():
+        l = ln[:, None].detach().requires_grad_(True)
+        torch.autograd.grad(nb_graphed_fn(l), l)
+
     out["dps_notebook_shape_case4"] = {
-        "workload": f"case4 shapes, {Tn} frames x {Pn} sensor points (the notebook's literal DPS shape), eager launches",
-        "autograd_ms": timed(nb_autograd, 10), "fused_loss_ms": timed(nb_fused, 10)}
+        "workload": f"case4 shapes, {Tn} frames x {Pn} sensor points (the notebook's literal DPS shape)",
+        "autograd_ms": timed(nb_autograd, 10), "fused_loss_ms": timed(nb_fused, 10),
+        "fused_loss_cuda_graph_ms": timed(nb_graphed, 10)}
     return out
 
 

@@ -11,14 +11,14 @@ from .nf_networks import (BatchLinear, Sine, SIRENAutodecoder_film, SIRENAutodec
                           canonicalize, first_layer_sine_init, sine_init, PRECISION_NOTES)
 from .inference_function import decoder, pass_through_model_batch  # noqa: F401
 from .folding import fold_normalizers  # noqa: F401
-from .dps import measurement_norm, sensor_rows  # noqa: F401
+from .dps import GraphedMeasurementNorm, measurement_norm, sensor_rows  # noqa: F401
 from .latent_sampler import DDPMSchedule, LatentUNet, generate_fields, sample_latents  # noqa: F401
 from .distributed import FusedGatherDecoder, all_gather_frames, decode_frame_sharded, shard_bounds  # noqa: F401
 
 __all__ = [
     "SIRENAutodecoder_film", "SIRENAutodecoder_film_extra_in", "BatchLinear", "Sine",
     "decoder", "pass_through_model_batch", "decode_frame_sharded", "all_gather_frames", "shard_bounds",
-    "FusedGatherDecoder", "fold_normalizers", "measurement_norm", "sensor_rows", "LatentUNet", "DDPMSchedule", "sample_latents", "generate_fields",
+    "FusedGatherDecoder", "fold_normalizers", "measurement_norm", "GraphedMeasurementNorm", "sensor_rows", "LatentUNet", "DDPMSchedule", "sample_latents", "generate_fields",
     "install",
 ]
 

@@ -257,6 +257,65 @@ def measurement_norm(model: SIRENAutodecoder_film, coords: torch.Tensor, latents
     return norm
 
 
+class _GraphReplay(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, latents, owner):
+        owner._lat.detach().copy_(latents.reshape(owner._lat.shape))
+        owner._graph.replay()
+        ctx.grad = owner._grad.clone().reshape(latents.shape)
+        return owner._norm.clone()
+
+    @staticmethod
+    def backward(ctx, gnorm):
+        return ctx.grad * gnorm, None
+
+
+class GraphedMeasurementNorm:
+    """``measurement_norm`` and its latent gradient captured ONCE in a CUDA graph for a guided-sampling loop whose
+    shapes, coordinates, measurement, mask and decoder weights do not change from step to step (the reference's DPS
+    loop: condition_methods.py:28-33 called a thousand times).  ``graphed(latents)`` copies the latents into the graph's
+    static input, replays K1 -> forward + loss -> finalize -> backward -> K4 and returns the norm as a scalar that is
+    differentiable with respect to ``latents`` (so ``torch.autograd.grad(norm, x_prev)`` through the U-Net works as
+    with ``measurement_norm``); one replay replaces ~25 Python-level launches and allocations per step.
+
+    ``latents`` fixes the shape (and must be a CUDA tensor); keyword arguments are those of ``measurement_norm``
+    (``return_field`` is not supported).  Re-create the object after changing the decoder's weights or ``w0``.
+    """
+
+    def __init__(self, model: SIRENAutodecoder_film, coords: torch.Tensor, latents: torch.Tensor,
+                 measurement: torch.Tensor, **kwargs):
+        if kwargs.get("return_field"):
+            raise ValueError("GraphedMeasurementNorm does not return the field")
+        if not latents.is_cuda:
+            raise ValueError("GraphedMeasurementNorm needs CUDA tensors")
+        if any(p.requires_grad for p in model.parameters()):
+            raise ValueError("freeze the decoder first (model.disable_gradient()): only the latents are differentiated")
+        self._lat = latents.detach().clone().requires_grad_(True)
+        self._keep = (model, coords, measurement, kwargs)  # the identity-keyed caches must stay valid
+
+        def step():
+            norm = measurement_norm(model, coords, self._lat, measurement, **kwargs)
+            (grad,) = torch.autograd.grad(norm, self._lat)
+            return norm, grad
+
+        dev = latents.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside capture: weight packing, caches, allocator
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            norm, grad = step()
+        self._norm, self._grad = norm.detach(), grad
+
+    def __call__(self, latents: torch.Tensor) -> torch.Tensor:
+        if latents.numel() != self._lat.numel() or latents.device != self._lat.device:
+            raise ValueError(f"latents must have {self._lat.numel()} elements on {self._lat.device}")
+        return _GraphReplay.apply(latents.to(torch.float32), self)
+
+
 def sensor_rows(coords: torch.Tensor, mask: torch.Tensor, *fields: torch.Tensor):
     """Gather the rows a per-point ``mask (P,)`` keeps: returns ``(coords[idx], idx, *[f[..., idx, :] for f in fields])``.
 

@@ -436,6 +436,35 @@ def test_dps_step_under_cuda_graph():
         assert O.rel_l2(grad_g, g_ref) <= 1e-2
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,T,P,sensors", [("case1", 16, 4000, 300), ("case4", 48, 10, 10)])
+def test_graphed_measurement_norm_replays_with_new_latents(case, T, P, sensors):
+    """GraphedMeasurementNorm: the fused DPS step captured once, replayed with new latents, differentiable through an
+    upstream op (stands in for the U-Net between x_prev and the latents)."""
+    dims = O.CASE_SHAPES[case]
+    sd = O.init_params(*dims, seed=0)
+    m = make_model(dims, sd, "f16f8")
+    m.disable_gradient()
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    c = coords.cuda()[None]
+    mask = torch.zeros(P, device="cuda")
+    mask[torch.randperm(P, generator=torch.Generator().manual_seed(0))[:sensors].cuda()] = 1.0
+    y_meas = (torch.randn(T, P, dims[2], generator=torch.Generator().manual_seed(3)) * 0.05).cuda()
+    graphed = cb.GraphedMeasurementNorm(m, c, lat.cuda()[:, None], y_meas, mask=mask)
+    for seed in (11, 12, 13):
+        new = (torch.randn(T, 1, dims[1], generator=torch.Generator().manual_seed(seed)) * 0.1).cuda()
+        x_prev = new.clone().requires_grad_(True)
+        n_g = graphed(1.5 * x_prev + 0.01)               # upstream op: the gradient must chain through it
+        (g_g,) = torch.autograd.grad(n_g, x_prev)
+        x2 = new.clone().requires_grad_(True)
+        n_e = cb.measurement_norm(m, c, 1.5 * x2 + 0.01, y_meas, mask=mask)
+        (g_e,) = torch.autograd.grad(n_e, x2)
+        assert abs(float(n_g) - float(n_e)) <= 1e-6 * float(n_e)
+        assert O.rel_l2(g_g, g_e) <= 1e-5
+    with pytest.raises(ValueError):
+        graphed(torch.zeros(T + 1, 1, dims[1], device="cuda"))
+
+
 def test_training_mode_with_grad_raises():
     m = cb.SIRENAutodecoder_film(2, 128, 3, 10, 128).cuda()  # training mode, params require grad
     with pytest.raises(NotImplementedError):

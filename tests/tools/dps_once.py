@@ -31,4 +31,13 @@ ts = []
 for _ in range(12):
     torch.cuda.synchronize(); t0 = time.perf_counter(); step(); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
 print("wall ms per step:", " ".join(f"{t:.2f}" for t in ts))
+graphed = cb.GraphedMeasurementNorm(m, c[None], l0[:, None], ym, mask=mask, zero_row_skip=(mode == "skip"))
+def gstep():
+    l = l0[:, None].detach().requires_grad_(True)
+    return torch.autograd.grad(graphed(l), l)[0]
+for _ in range(3): gstep()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(50): gg = gstep()
+torch.cuda.synchronize()
+print(f"graphed step: {(time.perf_counter() - t0) / 50 * 1e3:.3f} ms wall; rel diff of the gradient vs eager {float((gg - g).norm() / g.norm()):.2e}")
 print(f"{case} DPS step ({mode}, {m.resolved_precision}): {e0.elapsed_time(e1) / 5:.3f} ms; |g| = {float(g.norm()):.4e}")
