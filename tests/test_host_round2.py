@@ -78,3 +78,37 @@ def test_auto_precision_policy_resolution():
     assert cb.SIRENAutodecoder_film(2, 128, 3, 10, 128, precision="bf16x3").resolved_precision == "bf16x3"
     with pytest.raises(ValueError):
         cb.SIRENAutodecoder_film(2, 128, 3, 10, 128, precision="int4")._precision_code()
+
+
+def test_dps_loop_cache_is_keyed_on_identity_and_version():
+    """dps._cached: a hit needs the SAME tensor objects at the SAME in-place version; a new object (even at a recycled
+    address) or an in-place update rebuilds the entry."""
+    from confild_b200 import dps
+
+    dps._CACHE.clear()
+    calls = []
+
+    def make(tag):
+        def f():
+            calls.append(tag)
+            return len(calls)
+        return f
+
+    a, b = torch.zeros(4), torch.ones(4)
+    v1 = dps._cached("k", (a, b), (1,), make("first"))
+    assert dps._cached("k", (a, b), (1,), make("hit")) == v1 and calls == ["first"]
+    assert dps._cached("k", (a, b), (2,), make("other-extra")) != v1          # different shape key
+    a.add_(1.0)                                                                # in-place: version bump
+    v2 = dps._cached("k", (a, b), (1,), make("after-inplace"))
+    assert v2 != v1 and calls[-1] == "after-inplace"
+    assert dps._cached("k", (a, b), (1,), make("hit2")) == v2 and calls[-1] == "after-inplace"
+    c = a.clone()                                                              # equal content, different object
+    assert dps._cached("k", (c, b), (1,), make("clone")) != v2 and calls[-1] == "clone"
+    key_id = id(c)
+    del c
+    d = torch.zeros(4)                                                         # may reuse the freed object's id
+    got = dps._cached("k", (d, b), (1,), make("new-object"))
+    assert calls[-1] == "new-object" or id(d) != key_id, got
+    for i in range(dps._CACHE_MAX + 5):                                        # bounded
+        dps._cached("fill", (torch.zeros(1),), (i,), make("x"))
+    assert len(dps._CACHE) <= dps._CACHE_MAX
