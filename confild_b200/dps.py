@@ -48,7 +48,7 @@ ZERO_ROW_SKIP_MAX_FRACTION = 0.5
 # identity of the caller's tensor objects and validated by weak reference and in-place version counter, so a recycled
 # address or an in-place update can never produce a stale hit.
 _CACHE: dict = {}
-_CACHE_MAX = 64
+_CACHE_MAX = 32
 
 
 def _cached(name: str, tensors, extra: tuple, make):
@@ -60,6 +60,8 @@ def _cached(name: str, tensors, extra: tuple, make):
             return val
         del _CACHE[key]
     val = make()
+    for k in [k for k, (refs, _, _) in _CACHE.items() if any(r() is None for r in refs)]:
+        del _CACHE[k]  # entries whose source tensors are gone would only pin device memory
     if len(_CACHE) >= _CACHE_MAX:
         _CACHE.clear()
     _CACHE[key] = ([weakref.ref(t) for t in tensors], [t._version for t in tensors], val)
