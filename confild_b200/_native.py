@@ -109,7 +109,7 @@ def load() -> ctypes.CDLL:
     lib.cnf_group_norm_scratch_bytes.restype = sz
     lib.cnf_group_norm_scratch_bytes.argtypes = [i64]
     lib.cnf_group_norm_nhwc_bf16.restype = i32
-    lib.cnf_group_norm_nhwc_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, f32, i32, vp]
+    lib.cnf_group_norm_nhwc_bf16.argtypes = [vp, vp, i64, vp, vp, vp, vp, i64, i64, i32, i32, f32, i32, vp]
     if lib.cnf_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path}: ABI version {lib.cnf_abi_version()} != {ABI_VERSION}; rebuild with "
                            "`python -m confild_b200.build --force`")

@@ -34,8 +34,8 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 }
 
 __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__ x, const float* __restrict__ add,
-                                                       float* __restrict__ partials, int HW, int C, int G, int chunk_px,
-                                                       int chunks) {
+                                                       int64_t add_stride, float* __restrict__ partials, int HW, int C,
+                                                       int G, int chunk_px, int chunks) {
   extern __shared__ __align__(16) float sm[];  // [2][R][C]
   const int vecs = C / 8, R = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
   const int n = blockIdx.y, chunk = blockIdx.x;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__
   float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (add != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) e[j] = add[(size_t)n * C + tx * 8 + j];
+    for (int j = 0; j < 8; ++j) e[j] = add[(size_t)n * add_stride + tx * 8 + j];
   }
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const uint4* xp = x + (size_t)n * HW * vecs;
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const uint4* __restrict__
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ add,
-                                                       const float* __restrict__ partials,
+                                                       int64_t add_stride, const float* __restrict__ partials,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        uint4* __restrict__ y, int HW, int C, int G, int chunk_px,
                                                        int chunks, float eps, int silu) {
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
     const int g = c / (C / G);
     const float ga = gamma[c] * rstd[g];
     a[c] = ga;
-    b[c] = fmaf((add != nullptr ? add[(size_t)n * C + c] : 0.f) - mean[g], ga, beta[c]);
+    b[c] = fmaf((add != nullptr ? add[(size_t)n * add_stride + c] : 0.f) - mean[g], ga, beta[c]);
   }
   __syncthreads();
   float ra[8], rb[8];
@@ -150,9 +150,9 @@ extern "C" size_t cnf_group_norm_scratch_bytes(int64_t N) {
   return N <= 0 ? 0 : (size_t)N * cnf::kGnMaxChunks * cnf::kGnMaxGroups * 2 * sizeof(float);
 }
 
-extern "C" int cnf_group_norm_nhwc_bf16(const void* d_x, const float* d_add, const float* d_gamma, const float* d_beta,
-                                        void* d_y, float* d_partials, int64_t N, int64_t HW, int32_t C, int32_t groups,
-                                        float eps, int32_t silu, void* stream) {
+extern "C" int cnf_group_norm_nhwc_bf16(const void* d_x, const float* d_add, int64_t add_stride, const float* d_gamma,
+                                        const float* d_beta, void* d_y, float* d_partials, int64_t N, int64_t HW,
+                                        int32_t C, int32_t groups, float eps, int32_t silu, void* stream) {
   using namespace cnf;
   using cnf::host::fail;
   if (d_x == nullptr || d_y == nullptr || d_gamma == nullptr || d_beta == nullptr || d_partials == nullptr)
@@ -177,10 +177,11 @@ extern "C" int cnf_group_norm_nhwc_bf16(const void* d_x, const float* d_add, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem_stats = (size_t)2 * R * C * sizeof(float);
   const size_t smem_apply = ((size_t)2 * C + 2 * groups) * sizeof(float);
-  gn_stats_kernel<<<grid, block, smem_stats, st>>>(static_cast<const uint4*>(d_x), d_add, d_partials, (int)HW, C, groups,
-                                                   chunk_px, (int)chunks);
+  if (d_add != nullptr && add_stride < C) return fail(CNF_ERR_INVALID_ARGUMENT, "cnf_group_norm_nhwc_bf16: add_stride < C");
+  gn_stats_kernel<<<grid, block, smem_stats, st>>>(static_cast<const uint4*>(d_x), d_add, add_stride, d_partials, (int)HW,
+                                                   C, groups, chunk_px, (int)chunks);
   CNF_CUDA(cudaGetLastError());
-  gn_apply_kernel<<<grid, block, smem_apply, st>>>(static_cast<const uint4*>(d_x), d_add, d_partials, d_gamma, d_beta,
+  gn_apply_kernel<<<grid, block, smem_apply, st>>>(static_cast<const uint4*>(d_x), d_add, add_stride, d_partials, d_gamma, d_beta,
                                                    static_cast<uint4*>(d_y), (int)HW, C, groups, chunk_px, (int)chunks, eps,
                                                    silu);
   CNF_CUDA(cudaGetLastError());

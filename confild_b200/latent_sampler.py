@@ -43,7 +43,8 @@ from . import _native
 def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, num_groups: int, eps: float = 1e-5,
                     add: Optional[torch.Tensor] = None, silu: bool = False) -> torch.Tensor:
     """``act(GroupNorm(x + add[:, :, None, None]))`` for a CUDA bf16 channels-last ``x (N, C, H, W)`` with fp32
-    statistics (``cnf_group_norm_nhwc_bf16``); ``weight`` / ``bias`` fp32 ``(C,)``, ``add`` fp32 ``(N, C)`` or None.
+    statistics (``cnf_group_norm_nhwc_bf16``); ``weight`` / ``bias`` fp32 ``(C,)``, ``add`` fp32 ``(N, C)`` (rows may be
+    a column slice of a wider matrix: only the last dimension must be contiguous) or None.
     Inference only (no autograd).  Reference semantics: src/nn.py:17-19 (GroupNorm32) followed by nn.SiLU."""
     if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
         raise ValueError("group_norm_nhwc expects a 4-d CUDA bfloat16 tensor")
@@ -55,13 +56,15 @@ def group_norm_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, n
     if add is not None:
         if add.dtype != torch.float32 or tuple(add.shape) != (N, C):
             raise ValueError("group_norm_nhwc: add must be float32 of shape (N, C)")
-        add = add.contiguous()
+        if add.stride(1) != 1 or (N > 1 and add.stride(0) < C):
+            add = add.contiguous()
     lib = _native.load()
     y = torch.empty_like(x)  # preserves the channels-last strides
     scratch = torch.empty(max(1, lib.cnf_group_norm_scratch_bytes(N) // 4), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _native.check(lib.cnf_group_norm_nhwc_bf16(x.data_ptr(), None if add is None else add.data_ptr(),
+                                                   0 if add is None else (add.stride(0) if N > 1 else C),
                                                    weight.contiguous().data_ptr(), bias.contiguous().data_ptr(),
                                                    y.data_ptr(), scratch.data_ptr(), N, H * W, C, int(num_groups),
                                                    float(eps), int(bool(silu)), stream), "cnf_group_norm_nhwc_bf16")
@@ -235,6 +238,15 @@ class LatentUNet(nn.Module):
                 fast[m] = (m.weight.detach().to(bf).contiguous(), m.bias.detach().to(bf))
             elif isinstance(m, nn.GroupNorm):
                 fast[m] = (m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous())
+        # every residual block projects the same SiLU(time embedding): one GEMM for all of them (fp32 result, sliced)
+        res = [m for m in self.modules() if isinstance(m, _Res)]
+        fast["emb_w"] = torch.cat([m.emb_layers[1].weight.detach() for m in res], 0).to(bf).contiguous()
+        fast["emb_b"] = torch.cat([m.emb_layers[1].bias.detach() for m in res], 0).to(bf).contiguous()
+        off = 0
+        for m in res:
+            n = m.emb_layers[1].out_features
+            fast[("emb_slice", m)] = (off, off + n)
+            off += n
         self._fast = fast
         return self
 
@@ -259,11 +271,13 @@ class LatentUNet(nn.Module):
             return group_norm_nhwc(v, w, b, m.num_groups, m.eps, add=add, silu=silu)
 
         emb = lin(self.time_embed[2], F.silu(lin(self.time_embed[0], sinusoidal_embedding(timesteps, self.model_channels).to(bf))))
-        emb_act = F.silu(emb)  # every residual block starts its embedding branch with the same SiLU
+        # every residual block starts its embedding branch with the same SiLU -> Linear: one GEMM, fp32, sliced per block
+        emb_all = F.linear(F.silu(emb), fast["emb_w"], fast["emb_b"]).float()
 
         def res(m, v):
             h = conv(m.in_layers[2], gn(m.in_layers[0], v, True))
-            e = lin(m.emb_layers[1], emb_act).float()  # added inside the second normalisation, in fp32
+            lo, hi = fast[("emb_slice", m)]
+            e = emb_all[:, lo:hi]  # added inside the second normalisation, in fp32 (a strided view: no copy)
             h = conv(m.out_layers[3], gn(m.out_layers[0], h, True, add=e))
             return (v if isinstance(m.skip_connection, nn.Identity) else conv(m.skip_connection, v)) + h
 

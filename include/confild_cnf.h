@@ -187,15 +187,16 @@ int cnf_query_launch(const cnf_dims* dims, int precision, int64_t T, int64_t P, 
  * before the normalisation (the residual block's timestep-embedding add) and an optional SiLU:
  *     y[n,p,c] = act( ((x[n,p,c] + add[n,c]) - mean[n,g]) * rstd[n,g] * gamma[c] + beta[c] ),   g = c / (C/groups)
  * x, y: (N, HW, C) bf16 = a torch channels_last (N,C,H,W) tensor, 16-byte aligned, C a multiple of 8 and of `groups`
- * (<= 64); d_add NULL or (N, C) fp32; d_partials: scratch of cnf_group_norm_scratch_bytes(N) bytes.  Deterministic
+ * (<= 64); d_add NULL or fp32 rows of C values, row n at d_add + n * add_stride (a slice of a wider matrix);
+ * d_partials: scratch of cnf_group_norm_scratch_bytes(N) bytes.  Deterministic
  * (no atomics).  Replaces GroupNorm32 + SiLU of the guided-diffusion U-Net's blocks
  * (UnconditionalDiffusionTraining_and_Generation/src/nn.py:17-19, src/unet.py:185-200,228-256,283-300) in the
  * inference-only fast path of confild_b200.LatentUNet. */
 #define CNF_GN_MAX_CHUNKS 128
 size_t cnf_group_norm_scratch_bytes(int64_t N);
-int cnf_group_norm_nhwc_bf16(const void* d_x, const float* d_add, const float* d_gamma, const float* d_beta, void* d_y,
-                             float* d_partials, int64_t N, int64_t HW, int32_t C, int32_t groups, float eps,
-                             int32_t silu, void* stream);
+int cnf_group_norm_nhwc_bf16(const void* d_x, const float* d_add, int64_t add_stride, const float* d_gamma,
+                             const float* d_beta, void* d_y, float* d_partials, int64_t N, int64_t HW, int32_t C,
+                             int32_t groups, float eps, int32_t silu, void* stream);
 
 #ifdef __cplusplus
 }

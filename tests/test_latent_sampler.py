@@ -149,6 +149,10 @@ def test_group_norm_nhwc_kernel_vs_torch(shape, silu, with_add):
     assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
     got2 = group_norm_nhwc(x, w, b, 32, 1e-5, add=add, silu=silu)
     assert torch.equal(got, got2)  # deterministic: no atomics
+    if with_add:  # the pre-add as a column slice of a wider matrix (how forward_inference passes it)
+        wide = torch.randn(N, C + 24, device="cuda", generator=g)
+        wide[:, 8:8 + C] = add
+        assert torch.equal(group_norm_nhwc(x, w, b, 32, 1e-5, add=wide[:, 8:8 + C], silu=silu), got)
     err = (got.float() - want).abs()
     tol = 2.0 ** -7 * want.abs() + 2e-2
     assert bool((err <= tol).all()), float((err - tol).max())
