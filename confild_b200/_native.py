@@ -124,7 +124,7 @@ def check(rc: int, what: str) -> None:
 
 
 #: defaults of the debug knobs (cnf_set_debug_knob); the environment variables of the same names set the initial values
-KNOB_DEFAULTS = {"CNF_TC2": 1, "CNF_TC_STAGES": 0, "CNF_TC_PACKED": -1, "CNF_TC_CLUSTER": 1}
+KNOB_DEFAULTS = {"CNF_TC2": 1, "CNF_TC_STAGES": 0, "CNF_TC_PACKED": -1, "CNF_TC_CLUSTER": 1, "CNF_GN_CLUSTER": 256}
 
 
 def set_knob(name: str, value: int) -> None:

@@ -63,6 +63,7 @@ Knobs& mutable_knobs() {
     k.stages = env_int("CNF_TC_STAGES", 0);
     k.packed = env_int("CNF_TC_PACKED", -1);
     k.cluster = env_int("CNF_TC_CLUSTER", 1);
+    k.gn_cluster = env_int("CNF_GN_CLUSTER", 256);
   });
   return k;
 }
@@ -74,6 +75,7 @@ int set_knob(const char* name, int value) {
   else if (!strcmp(name, "CNF_TC_STAGES")) k.stages = value;
   else if (!strcmp(name, "CNF_TC_PACKED")) k.packed = value;
   else if (!strcmp(name, "CNF_TC_CLUSTER")) k.cluster = value;
+  else if (!strcmp(name, "CNF_GN_CLUSTER")) k.gn_cluster = value;
   else return fail(CNF_ERR_INVALID_ARGUMENT, "unknown debug knob %s", name);
   return CNF_OK;
 }

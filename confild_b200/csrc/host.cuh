@@ -42,6 +42,7 @@ struct Knobs {
   int stages = 0;
   int packed = -1;
   int cluster = 1;  // CNF_TC_CLUSTER: H = 256/384 forward as CTA pairs: 1 = multicast weight stages (default), 2 = cta_group::2 MMAs, 0 = single CTAs
+  int gn_cluster = 256;  // CNF_GN_CLUSTER: GroupNorm of activations up to this many KiB per sample as ONE 8-CTA-cluster launch (0 = always two kernels)
 };
 const Knobs& knobs();
 int set_knob(const char* name, int value);  // tests / tuning: override a knob at run time

@@ -14,10 +14,16 @@
 //             written to partials[n][chunk][g][2]
 //   gn_apply  every block re-reduces its sample's <= 128 chunk partials into (mean, rstd), folds gamma / beta / the
 //             pre-add into one (a_c, b_c) pair per channel and streams y = act(a_c x + b_c).
+// Small activations (<= 256 KiB per sample: the 8x8 / 16x16 levels of the U-Net) take ONE kernel instead: gn_cluster, one
+// thread-block cluster of 8 CTAs per sample -- statistics of the CTA's pixels -> shared memory, barrier.cluster, every
+// CTA sums the 8 partial results over distributed shared memory in a fixed order, applies.  Measured over the 71 sites
+// of the case1 U-Net replayed from a CUDA graph (tests/tools/gn_ab.py): 864 us two kernels everywhere, 811 us with the
+// cluster path up to 256 KiB, 887 / 1,017 / 1,102 us with it up to 512 KiB / 1 MiB / 2 MiB (16 CTAs are too few there).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "host.cuh"
+#include "ptx.cuh"
 
 namespace cnf {
 constexpr int kGnMaxChunks = CNF_GN_MAX_CHUNKS;
@@ -143,6 +149,110 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const uint4* __restrict__
   }
 }
 
+constexpr int kGnCluster = 8;
+
+__global__ void __launch_bounds__(256) gn_cluster_kernel(const uint4* __restrict__ x, const float* __restrict__ add,
+                                                         int64_t add_stride, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, uint4* __restrict__ y, int HW,
+                                                         int C, int G, int chunk_px, float eps, int silu) {
+  extern __shared__ __align__(16) float sm[];  // [2][R][C] channel sums, reused as a[C], b[C]; then part[G][2], stat[G][2]
+  const int vecs = C / 8, R = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
+  const int n = blockIdx.y;
+  const uint32_t rank = ptx::cluster_ctarank();
+  float* part = sm + (size_t)2 * R * C;  // this CTA's per-group (sum, sum of squares): read by the whole cluster
+  float* stat = part + 2 * G;            // (mean, rstd) per group
+  const int p0 = (int)rank * chunk_px, p1 = min(HW, p0 + chunk_px);
+  const int tid = ty * vecs + tx, nthreads = vecs * R;
+  float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (add != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = add[(size_t)n * add_stride + tx * 8 + j];
+  }
+  const uint4* xp = x + (size_t)n * HW * vecs;
+  {
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = p0 + ty; p < p1; p += R) {
+      float f[8];
+      unpack8(__ldg(xp + (size_t)p * vecs + tx), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = f[j] + e[j];
+        s[j] += v;
+        q[j] = fmaf(v, v, q[j]);
+      }
+    }
+    float4* ps = reinterpret_cast<float4*>(sm + (size_t)ty * C + tx * 8);
+    float4* pq = reinterpret_cast<float4*>(sm + (size_t)(R + ty) * C + tx * 8);
+    ps[0] = make_float4(s[0], s[1], s[2], s[3]);
+    ps[1] = make_float4(s[4], s[5], s[6], s[7]);
+    pq[0] = make_float4(q[0], q[1], q[2], q[3]);
+    pq[1] = make_float4(q[4], q[5], q[6], q[7]);
+  }
+  __syncthreads();
+  if (tid < G) {
+    const int Cg = C / G;
+    float S = 0.f, Q = 0.f;
+    for (int r = 0; r < R; ++r)
+      for (int c = tid * Cg; c < (tid + 1) * Cg; ++c) {
+        S += sm[(size_t)r * C + c];
+        Q += sm[(size_t)(R + r) * C + c];
+      }
+    part[2 * tid] = S;
+    part[2 * tid + 1] = Q;
+  }
+  ptx::cluster_sync_all();  // every CTA's part[] is written (release / acquire at cluster scope)
+  if (tid < G) {
+    float S = 0.f, Q = 0.f;
+    const uint32_t local = ptx::smem_u32(part + 2 * tid);
+    for (uint32_t r = 0; r < (uint32_t)kGnCluster; ++r) {  // fixed order: identical (mean, rstd) in all CTAs, run to run
+      const uint32_t remote = ptx::mapa_shared(local, r);
+      float a, b;
+      asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(remote));
+      S += a;
+      Q += b;
+    }
+    const float inv_cnt = 1.f / ((float)HW * (float)(C / G));
+    const float m = S * inv_cnt;
+    stat[2 * tid] = m;
+    stat[2 * tid + 1] = rsqrtf(fmaxf(fmaf(-m, m, Q * inv_cnt), 0.f) + eps);
+  }
+  __syncthreads();
+  float* a = sm;  // the channel sums are consumed: reuse
+  float* b = sm + C;
+  for (int c = tid; c < C; c += nthreads) {
+    const int g = c / (C / G);
+    const float ga = gamma[c] * stat[2 * g + 1];
+    a[c] = ga;
+    b[c] = fmaf((add != nullptr ? add[(size_t)n * add_stride + c] : 0.f) - stat[2 * g], ga, beta[c]);
+  }
+  __syncthreads();
+  float ra[8], rb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ra[j] = a[tx * 8 + j];
+    rb[j] = b[tx * 8 + j];
+  }
+  uint4* yp = y + (size_t)n * HW * vecs;
+  for (int p = p0 + ty; p < p1; p += R) {
+    float f[8];
+    unpack8(__ldg(xp + (size_t)p * vecs + tx), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = fmaf(f[j], ra[j], rb[j]);
+      if (silu) v = __fdividef(v, 1.f + __expf(-v));
+      f[j] = v;
+    }
+    uint4 o;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(f[0], f[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(f[2], f[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(f[4], f[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(f[6], f[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+    yp[(size_t)p * vecs + tx] = o;
+  }
+  ptx::cluster_sync_all();  // nobody's part[] may disappear (CTA exit) while a peer still reads it
+}
+
 }  // namespace
 }  // namespace cnf
 
@@ -175,9 +285,28 @@ extern "C" int cnf_group_norm_nhwc_bf16(const void* d_x, const float* d_add, int
   chunks = (HW + chunk_px - 1) / chunk_px;
   const dim3 grid((unsigned)chunks, (unsigned)N), block((unsigned)vecs, (unsigned)R);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d_add != nullptr && add_stride < C) return fail(CNF_ERR_INVALID_ARGUMENT, "cnf_group_norm_nhwc_bf16: add_stride < C");
+  // small activation: one cluster of kGnCluster CTAs per sample, a single launch (see the header comment)
+  if ((size_t)HW * C * 2 <= ((size_t)cnf::host::knobs().gn_cluster << 10)) {  // knob = threshold in KiB per sample
+    const int cpx = (int)((HW + kGnCluster - 1) / kGnCluster);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kGnCluster, (unsigned)N);
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = ((size_t)2 * R * C + 4 * groups) * sizeof(float);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kGnCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CNF_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, static_cast<const uint4*>(d_x), d_add, add_stride, d_gamma, d_beta,
+                                static_cast<uint4*>(d_y), (int)HW, (int)C, (int)groups, cpx, eps, (int)silu));
+    return CNF_OK;
+  }
   const size_t smem_stats = (size_t)2 * R * C * sizeof(float);
   const size_t smem_apply = ((size_t)2 * C + 2 * groups) * sizeof(float);
-  if (d_add != nullptr && add_stride < C) return fail(CNF_ERR_INVALID_ARGUMENT, "cnf_group_norm_nhwc_bf16: add_stride < C");
   gn_stats_kernel<<<grid, block, smem_stats, st>>>(static_cast<const uint4*>(d_x), d_add, add_stride, d_partials, (int)HW,
                                                    C, groups, chunk_px, (int)chunks);
   CNF_CUDA(cudaGetLastError());

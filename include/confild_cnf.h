@@ -70,7 +70,9 @@ const char* cnf_last_error(void);
  *   "CNF_TC_STAGES"  n: cap the depth of the shared-memory weight ring (default 0 = as deep as fits)
  *   "CNF_TC_PACKED"  0/1: force frame-aligned / packed tiles (default -1 = by shape)
  *   "CNF_TC_CLUSTER" H = 256/384 forward: 1 = CTA pairs with multicast weight stages (default), 2 = CTA pairs driven by
- *                    cta_group::2 MMAs (correct, measured ~10 % slower: DESIGN.md section 4), 0 = single CTAs */
+ *                    cta_group::2 MMAs (correct, measured ~10 % slower: DESIGN.md section 4), 0 = single CTAs
+ *   "CNF_GN_CLUSTER" n: cnf_group_norm_nhwc_bf16 runs activations of up to n KiB per sample as ONE launch of an 8-CTA
+ *                    cluster per sample (default 256), larger ones as two kernels (statistics, then apply); 0 = always two */
 int cnf_set_debug_knob(const char* name, int value);
 
 /* 1 if the tensor-core (tcgen05) kernels exist for these dims, else 0 (CUDA-core fp32 only). */

@@ -149,6 +149,20 @@ def test_group_norm_nhwc_kernel_vs_torch(shape, silu, with_add):
     assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
     got2 = group_norm_nhwc(x, w, b, 32, 1e-5, add=add, silu=silu)
     assert torch.equal(got, got2)  # deterministic: no atomics
+    tol = 2.0 ** -7 * want.abs() + 2e-2
+    # both paths on every shape: two kernels (knob 0) and the single-launch 8-CTA cluster (threshold above any size here);
+    # they may differ by fp32 summation order only
+    from confild_b200 import _native
+    try:
+        _native.set_knob("CNF_GN_CLUSTER", 0)
+        got_two = group_norm_nhwc(x, w, b, 32, 1e-5, add=add, silu=silu)
+        _native.set_knob("CNF_GN_CLUSTER", 1 << 20)
+        got_cl = group_norm_nhwc(x, w, b, 32, 1e-5, add=add, silu=silu)
+    finally:
+        _native.set_knob("CNF_GN_CLUSTER", _native.KNOB_DEFAULTS["CNF_GN_CLUSTER"])
+    for other in (got_two, got_cl):
+        assert bool(((other.float() - want).abs() <= tol).all())
+        assert float((other.float() - got.float()).abs().max()) <= 2.0 ** -6 * max(1.0, float(want.abs().max()))
     if with_add:  # the pre-add as a column slice of a wider matrix (how forward_inference passes it)
         wide = torch.randn(N, C + 24, device="cuda", generator=g)
         wide[:, 8:8 + C] = add
