@@ -335,10 +335,16 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
 
-// Residuals x - bf16(x) of the two values packed in `hi` (cvt.rn.bf16x2: x0 in the low half), packed as bf16x2.
-// One fma.f32x2 for both columns (exact: x - h = fma(h, -1, x)) instead of two scalar subtractions.
+// Residuals x - bf16(x) of the two values packed in `hi` (cvt.rn.bf16x2: x0 in the low half).
+// sm_100 mixed-precision FMA (fma.rn.f32.bf16: 16-bit a, b, fp32 c and result): SASS FHFMA reads the 16-bit half straight
+// out of the packed register (.H0 / .H1 selectors), so x - h = fma(h, -1, x) is ONE instruction per value with no unpack
+// (before: shift / mask to widen each half + one fma.f32x2 per pair = 1.5 instructions per value).  Exact, as before.
 __device__ __forceinline__ float2 bf16x2_residual(uint32_t hi, float x0, float x1) {
-  return __ffma2_rn(make_float2(bf16lo_to_f32(hi), bf16hi_to_f32(hi)), make_float2(-1.f, -1.f), make_float2(x0, x1));
+  float2 r;
+  const unsigned short h0 = (unsigned short)(hi & 0xffffu), h1 = (unsigned short)(hi >> 16);
+  asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(r.x) : "h"(h0), "h"((unsigned short)0xBF80), "f"(x0));  // 0xBF80 = -1.0
+  asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(r.y) : "h"(h1), "h"((unsigned short)0xBF80), "f"(x1));
+  return r;
 }
 
 // Four fp32 values -> four 8-bit floats in one word (x0 in byte 0).  cvt.*x2 puts its FIRST source in the upper byte.
@@ -366,8 +372,11 @@ __device__ __forceinline__ uint32_t pack_e5m2x4(float x0, float x1, float x2, fl
 }
 // Residuals x - fp16(x) of the two values packed in `hi` (cvt.rn.f16x2: x0 in the low half): one fma.f32x2.
 __device__ __forceinline__ float2 f16x2_residual(uint32_t hi, float x0, float x1) {
-  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-  return __ffma2_rn(h, make_float2(-1.f, -1.f), make_float2(x0, x1));
+  float2 r;  // fma.rn.f32.f16 (FHFMA): see bf16x2_residual
+  const unsigned short h0 = (unsigned short)(hi & 0xffffu), h1 = (unsigned short)(hi >> 16);
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r.x) : "h"(h0), "h"((unsigned short)0xBC00), "f"(x0));  // 0xBC00 = -1.0
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r.y) : "h"(h1), "h"((unsigned short)0xBC00), "f"(x1));
+  return r;
 }
 
 // "Pinned" variants: volatile asm keeps the program order of MUFU and pack instructions relative to each other, so a
