@@ -16,6 +16,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "layout.cuh"
 #include "ptx.cuh"
 #include "tc_common.cuh"
@@ -35,7 +37,7 @@ struct Tc2SmemTail {
   float shift_s[2][2][kTc2H];   // [slot][layer parity][column]
   float y_part[2][kTileM][4];   // head partial sums of the upper column half, per slot
   float y_stage[2][kTileM * 4]; // the tile's decoded values [row][cout], staged for the vectorised store
-  float w_first_s[kTc2H * 4];
+  float w_first_s[4 * kTc2H];  // [cin][H]
   float w_out_s[4 * kTc2H];
   uint64_t b_full[kTcMaxStages];
   uint64_t b_empty[kTcMaxStages];
@@ -262,7 +264,8 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
   {  // small fp32 operands of layer 0 and of the head, once per CTA
     const float* w_first = reinterpret_cast<const float*>(packed + lay.w_first);
     const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
-    for (int i = threadIdx.x; i < H * cin; i += kTc2Threads) tail->w_first_s[i] = w_first[i];
+    // coordinate-major in shared memory ([cin][H]): layer 0 reads four columns of one coordinate with one LDS.128
+    for (int i = threadIdx.x; i < H * cin; i += kTc2Threads) tail->w_first_s[(i % cin) * H + i / cin] = w_first[i];
     for (int i = threadIdx.x; i < cout * H; i += kTc2Threads) tail->w_out_s[i] = w_out[i];
     if (kF8) {
       const float* sc = reinterpret_cast<const float*>(packed + lay.tc_scale);
@@ -318,21 +321,36 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         ptx::bar_sync(bar_wg, 128);
       }
 
-      // ---- layer 0 on CUDA cores (K = cin), always range-reduced
+      // ---- layer 0 on CUDA cores (K = cin), always range-reduced.  The body is instantiated per cin: with a run-time
+      // cin the predicated-off FMAs and loads of the missing coordinates still took issue slots, and the scalar
+      // shared-memory loads made it 19 instructions per element against 7 in a hidden layer -- a fifth of the kernel's
+      // instructions.  Same FMA order as before (shift, then coordinate 0, 1, ..): bit-identical results.
+      auto layer0 = [&](auto cin_tag) {
+      constexpr int CIN = decltype(cin_tag)::value;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int c0 = 32 * hf + 64 * half;
         float h[32];
         [[maybe_unused]] float cs0[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float z = PACKED ? __ldg(sh + c0 + j) : tail->shift_s[g][0][c0 + j];
+        for (int j = 0; j < 32; j += 4) {
+          const float4 s4 = PACKED ? __ldg(reinterpret_cast<const float4*>(sh + c0 + j))
+                                   : *reinterpret_cast<const float4*>(&tail->shift_s[g][0][c0 + j]);
+          float z[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < cin) z = fmaf(tail->w_first_s[(c0 + j) * cin + i], x[i], z);
-          const float r = ptx::reduce_2pi(z);
-          h[j] = ptx::sin_approx(r);
-          if (STASH) cs0[j] = ptx::cos_approx(r);
+          for (int i = 0; i < CIN; ++i) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&tail->w_first_s[i * kTc2H + c0 + j]);
+            z[0] = fmaf(w4.x, x[i], z[0]);
+            z[1] = fmaf(w4.y, x[i], z[1]);
+            z[2] = fmaf(w4.z, x[i], z[2]);
+            z[3] = fmaf(w4.w, x[i], z[3]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float r = ptx::reduce_2pi(z[k]);
+            h[j + k] = ptx::sin_approx(r);
+            if (STASH) cs0[j + k] = ptx::cos_approx(r);
+          }
         }
         tc2_store_a<PREC, !STASH>(tmem_a, c0, h);
         if (STASH) {
@@ -348,6 +366,13 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
         ptx::tc_fence_before();
         if (half == 1 && tc2_quarter_issue(PREC)) ptx::mbar_arrive(&tail->a_q3[g]);
         ptx::mbar_arrive(half == 0 ? &tail->a_half[g] : &tail->a_full[g]);  // K slab `half` of the A operand is in TMEM
+      }
+      };
+      switch (cin) {
+        case 1: layer0(std::integral_constant<int, 1>{}); break;
+        case 2: layer0(std::integral_constant<int, 2>{}); break;
+        case 3: layer0(std::integral_constant<int, 3>{}); break;
+        default: layer0(std::integral_constant<int, 4>{}); break;
       }
       if (tracer) CNF_TRACE_EVENT(trole, 101);  // layer 0 done, a_full arrived
 
