@@ -36,6 +36,7 @@ struct PackedLayout {
   // [e4m3(S w)[k 0..63] | e4m3(S w - fp16(S w))[k 0..63]] of that slab; S_l = a power of two per layer
   size_t tc_fwd_f8;  // [nl][stages_per_layer(H,2)][16 KiB]
   size_t tc_scale;   // [2*nl] fp32: 1/S_l for l < nl, then S_l
+  size_t w_first_t;  // [4][H] fp32: w_first coordinate-major, rows >= cin zero (16-byte loads in the kernels' layer 0)
   size_t total;
 };
 
@@ -62,6 +63,7 @@ __host__ __device__ inline PackedLayout make_layout(const cnf_dims& d) {
     p.tc_fwd_f8 = take(nl * (size_t)stages_per_layer(d.H, 2) * kStageBytes);
     p.tc_scale = take(2 * nl * sizeof(float));
   }
+  p.w_first_t = take(4 * H * 4);
   p.total = off;
   return p;
 }

@@ -24,6 +24,11 @@ __global__ void pack_fp32_kernel(cnf_dims d, const float* __restrict__ params, f
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (size_t i = tid; i < H * d.cin; i += stride) w_first[i] = w0 * params[po.w_first + i];
+  float* w_first_t = reinterpret_cast<float*>(packed + lay.w_first_t);
+  for (size_t i = tid; i < 4 * H; i += stride) {
+    const size_t c = i / H, n = i % H;
+    w_first_t[i] = c < (size_t)d.cin ? w0 * params[po.w_first + n * d.cin + c] : 0.f;
+  }
   for (size_t i = tid; i < (size_t)d.cout * H; i += stride) w_out[i] = params[po.w_out + i];
   for (size_t i = tid; i < (size_t)d.cout; i += stride) b_out[i] = params[po.b_out + i];
   for (size_t i = tid; i < (nl + 1) * H; i += stride) {

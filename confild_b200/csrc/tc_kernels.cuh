@@ -19,6 +19,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "layout.cuh"
 #include "ptx.cuh"
 #include "tc_common.cuh"
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
     const int cg = warp / 4, wq = warp % 4;
     const int row = wq * 32 + lane;
     const int col_lo = cg * C::kColsPerGroup, col_hi = col_lo + C::kColsPerGroup;
-    const float* w_first = reinterpret_cast<const float*>(packed + lay.w_first);
+    const float* w_first_t = reinterpret_cast<const float*>(packed + lay.w_first_t);  // [4][H], coordinate-major
     const float* w_out = reinterpret_cast<const float*>(packed + lay.w_out);
     const float* b_out = reinterpret_cast<const float*>(packed + lay.b_out);
     const uint32_t tmem_row = tmem_base + ((uint32_t)(wq * 32) << 16);
@@ -644,6 +646,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         ptx::tc_fence_before();
         for (int n = 1; n < C::kNBlocks; ++n) tc_epi_arrive<CM>(&tail->d_drained[n]);
       }
+      // Instantiated per cin, 16-byte loads of the shifts and of the coordinate-major first-layer weights (w_first_t):
+      // with a run-time cin and scalar loads this loop was ~19 instructions per element, and it sits in the tile-boundary
+      // bubble of the tensor pipe.  Same FMA order as before (shift, coordinate 0, 1, ..): bit-identical results.
+      auto layer0 = [&](auto cin_tag) {
+      constexpr int CIN = decltype(cin_tag)::value;
 #pragma unroll 1
       for (int c = 0; c < C::kColsPerGroup / 16; ++c) {
         // block pipeline: this thread's columns are [128n + 32cg, +32) of every K part n, part 0 first
@@ -651,14 +658,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
         float h[16];
         [[maybe_unused]] float cs[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float z = __ldg(sh + c0 + j);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sh + c0 + j));
+          float z[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < cin) z = fmaf(__ldg(w_first + (c0 + j) * cin + i), x[i], z);
-          const float r = ptx::reduce_2pi(z);
-          h[j] = ptx::sin_approx(r);
-          if (STASH) cs[j] = ptx::cos_approx(r);
+          for (int i = 0; i < CIN; ++i) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(w_first_t + i * H + c0 + j));
+            z[0] = fmaf(w4.x, x[i], z[0]);
+            z[1] = fmaf(w4.y, x[i], z[1]);
+            z[2] = fmaf(w4.z, x[i], z[2]);
+            z[3] = fmaf(w4.w, x[i], z[3]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float r = ptx::reduce_2pi(z[k]);
+            h[j + k] = ptx::sin_approx(r);
+            if (STASH) cs[j + k] = ptx::cos_approx(r);
+          }
         }
         tc_store_a16<H, PREC>(a_smem, tmem_row, row, c0, h);
         if (STASH) tc_stash16(st_row + (size_t)c0 * kTileM, cs);
@@ -668,6 +684,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
           ptx::fence_proxy_async_smem();
           tc_epi_arrive<CM>(&tail->e_done[c / 2]);
         }
+      }
+      };
+      switch (cin) {
+        case 1: layer0(std::integral_constant<int, 1>{}); break;
+        case 2: layer0(std::integral_constant<int, 2>{}); break;
+        case 3: layer0(std::integral_constant<int, 3>{}); break;
+        default: layer0(std::integral_constant<int, 4>{}); break;
       }
       if (!C::kBlockPipe) {
         ptx::tmem_wait_st();
