@@ -152,21 +152,21 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
                                                  HalfHook on_half = HalfHook()) {
   constexpr bool SCALED = (PREC == CNF_PREC_F16F8);
   uint32_t v[2][16];
-  float hcur[16], hnext[16];
+  float hb[2][16];  // sines of group c in hb[c & 1] (the loop is fully unrolled: both are register arrays, no copies)
   ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, 0), v[0]);
   ptx::tmem_wait_ld();
   ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, 1), v[1]);
-  tc_sines16<STASH, SCALED>(v[0], sbuf + tc2_group_col(hf, 0), hnext,
+  tc_sines16<STASH, SCALED>(v[0], sbuf + tc2_group_col(hf, 0), hb[0],
                             STASH ? stash_l + (size_t)tc2_group_col(hf, 0) * kTileM : nullptr, inv);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int c0 = tc2_group_col(hf, c);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) hcur[j] = hnext[j];
+    float(&hcur)[16] = hb[c & 1];
     if (c + 1 < 4) {
       const int c1 = tc2_group_col(hf, c + 1);
       ptx::tmem_wait_ld();
-      tc_sines16<STASH, SCALED>(v[(c + 1) & 1], sbuf + c1, hnext, STASH ? stash_l + (size_t)c1 * kTileM : nullptr, inv);
+      tc_sines16<STASH, SCALED>(v[(c + 1) & 1], sbuf + c1, hb[(c + 1) & 1],
+                                STASH ? stash_l + (size_t)c1 * kTileM : nullptr, inv);
       if (c + 2 < 4) ptx::tmem_ld_32x32b_x16(lane_base + tc2_group_col(hf, c + 2), v[c & 1]);
     }
     if (!LAST) {
