@@ -144,12 +144,15 @@ __host__ __device__ constexpr bool tc2_quarter_issue(int prec) { return prec == 
 struct Tc2NoHook {
   __device__ __forceinline__ void operator()() const {}
 };
-template <int PREC, bool LAST, bool STASH, typename HalfHook = Tc2NoHook>
-__device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tmem_a, int hf,
-                                                 const float* __restrict__ sbuf, const float* __restrict__ w_out_s,
-                                                 int cout, float (&y)[4], __half* stash_l, uint64_t* a_half,
-                                                 uint64_t* a_q3, uint64_t* a_full, float inv = 1.f,
-                                                 HalfHook on_half = HalfHook()) {
+// HF (the warpgroup's column half) is a template parameter: every column offset -- TMEM addresses, shift and head-weight
+// loads, stash offsets -- is then an immediate; with a run-time hf the layer spent ~40 of its ~440 instructions per
+// thread recomputing them (LOP3 / IADD3 / IMAD / LEA / R2UR).
+template <int PREC, bool LAST, bool STASH, int HF, typename HalfHook>
+__device__ __forceinline__ void tc2_hidden_layer_hf(uint32_t lane_base, uint32_t tmem_a,
+                                                    const float* __restrict__ sbuf, const float* __restrict__ w_out_s,
+                                                    int cout, float (&y)[4], __half* stash_l, uint64_t* a_half,
+                                                    uint64_t* a_q3, uint64_t* a_full, float inv, HalfHook on_half) {
+  constexpr int hf = HF;
   constexpr bool SCALED = (PREC == CNF_PREC_F16F8);
   uint32_t v[2][16];
   float hb[2][16];  // sines of group c in hb[c & 1] (the loop is fully unrolled: both are register arrays, no copies)
@@ -214,6 +217,20 @@ __device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tm
       }
     }
   }
+}
+
+template <int PREC, bool LAST, bool STASH, typename HalfHook = Tc2NoHook>
+__device__ __forceinline__ void tc2_hidden_layer(uint32_t lane_base, uint32_t tmem_a, int hf,
+                                                 const float* __restrict__ sbuf, const float* __restrict__ w_out_s,
+                                                 int cout, float (&y)[4], __half* stash_l, uint64_t* a_half,
+                                                 uint64_t* a_q3, uint64_t* a_full, float inv = 1.f,
+                                                 HalfHook on_half = HalfHook()) {
+  if (hf == 0)  // warp-uniform
+    tc2_hidden_layer_hf<PREC, LAST, STASH, 0>(lane_base, tmem_a, sbuf, w_out_s, cout, y, stash_l, a_half, a_q3, a_full, inv,
+                                              on_half);
+  else
+    tc2_hidden_layer_hf<PREC, LAST, STASH, 1>(lane_base, tmem_a, sbuf, w_out_s, cout, y, stash_l, a_half, a_q3, a_full, inv,
+                                              on_half);
 }
 
 template <int PREC, bool STASH, bool PACKED>
