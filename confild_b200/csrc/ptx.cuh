@@ -408,6 +408,9 @@ __device__ __forceinline__ float cos_approx(float x) {
 }
 // Cody-Waite reduction of x to [-pi, pi] with a two-constant 2*pi, rounding via the 1.5*2^23 trick
 // (no F2F/FRND on the XU pipe), so MUFU sees a small argument whatever the size of the pre-activation.
+// TWO_CONSTANTS = false drops the correction with 2*pi - fp32(2*pi): an argument error of |n| * 1.75e-7 (|n| <= ~10 turns in
+// layer 0), i.e. <= 2e-6 -- used by the precisions whose own error is 1e-5 or more (f16f8, fp16), one FMA less per value.
+template <bool TWO_CONSTANTS = true>
 __device__ __forceinline__ float reduce_2pi(float x) {
   const float kInv2Pi = 0.15915494309189535f;
   const float kMagic = 12582912.0f;        // 1.5 * 2^23
@@ -415,7 +418,7 @@ __device__ __forceinline__ float reduce_2pi(float x) {
   const float k2PiLo = -1.7484555e-07f;       // 2*pi - fp32(2*pi)
   float n = __fmaf_rn(x, kInv2Pi, kMagic) - kMagic;
   float r = __fmaf_rn(n, -k2PiHi, x);
-  return __fmaf_rn(n, -k2PiLo, r);
+  return TWO_CONSTANTS ? __fmaf_rn(n, -k2PiLo, r) : r;
 }
 
 }  // namespace ptx

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_forward_kernel(cnf_dims d,
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float r = ptx::reduce_2pi(z[k]);
+            const float r = ptx::reduce_2pi<PREC == CNF_PREC_BF16X3>(z[k]);
             h[j + k] = ptx::sin_approx(r);
             if (STASH) cs0[j + k] = ptx::cos_approx(r);
           }

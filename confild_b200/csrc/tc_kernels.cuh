@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_forward_kernel(cnf_dims d, c
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float r = ptx::reduce_2pi(z[k]);
+            const float r = ptx::reduce_2pi<PREC == CNF_PREC_BF16X3>(z[k]);
             h[j + k] = ptx::sin_approx(r);
             if (STASH) cs[j + k] = ptx::cos_approx(r);
           }
