@@ -42,6 +42,13 @@ def test_sizes_and_argument_checks(lib):
     assert lib.cnf_forward(d, None, 1, None, 0, None, None, 1, 1, None, 0, None) == 1
     assert lib.cnf_backward(d, None, 1, None, None, 0, None, 1, 1, None) == 1
     assert lib.cnf_film_shift(d, None, None, 1, None, None) == 1
+    # the sampler-side GroupNorm entry point: scratch size, NULL pointers and unsupported channel counts
+    assert lib.cnf_group_norm_scratch_bytes(2) == 2 * 128 * 64 * 2 * 4 and lib.cnf_group_norm_scratch_bytes(0) == 0
+    assert lib.cnf_group_norm_nhwc_bf16(None, None, 0, None, None, None, None, 2, 64, 128, 32, 1e-5, 1, None) == 1
+    fake = ctypes.c_void_p(0x1000)  # non-NULL, 16-byte aligned, never dereferenced: the shape check fails first
+    assert lib.cnf_group_norm_nhwc_bf16(fake, None, 0, fake, fake, fake, fake, 2, 64, 20, 4, 1e-5, 1, None) == 2
+    assert b"multiple of 8" in lib.cnf_last_error()
+    assert lib.cnf_group_norm_nhwc_bf16(fake, None, 0, fake, fake, fake, fake, 0, 64, 128, 32, 1e-5, 1, None) == 0  # N = 0
 
 
 def test_sass_has_tcgen05_and_bulk_tma():
@@ -57,3 +64,5 @@ def test_sass_has_tcgen05_and_bulk_tma():
     assert "LDTM" in sass         # tcgen05.ld
     assert "UBLKCP" in sass       # cp.async.bulk (1-D TMA)
     assert "MUFU.SIN" in sass
+    assert "UTCQMMA" in sass      # tcgen05.mma kind::f8f6f4 (the f16f8 precision's correction products)
+    assert "FHFMA" in sass        # mixed-precision fma.rn.f32.f16 / .bf16 (operand residuals)
