@@ -490,7 +490,9 @@ def test_forward_is_bitwise_reproducible_and_grad_mode_invariant(case, T, P):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dims", [(2, 16, 3, 1, 128), (2, 16, 3, 2, 128), (3, 8, 2, 1, 256), (2, 8, 4, 2, 384)])
+@pytest.mark.parametrize("dims", [(2, 16, 3, 1, 128), (2, 16, 3, 2, 128), (3, 8, 2, 1, 256), (2, 8, 4, 2, 384),
+                                  # every coordinate count has its own instantiation of layer 0 (cin = 1 .. 4)
+                                  (1, 16, 3, 2, 128), (4, 16, 1, 3, 128), (1, 8, 2, 2, 256), (4, 8, 3, 2, 256)])
 @pytest.mark.parametrize("prec", ["bf16x3", "fp16", "f16f8"])
 def test_shallow_networks_forward_and_gradient(dims, prec):
     """nl = 1 / 2: the issue schedules (half-layer, block pipeline) start and end inside one or two hidden layers;
