@@ -56,16 +56,34 @@ def _cached(name: str, tensors, extra: tuple, make):
     ent = _CACHE.get(key)
     if ent is not None:
         refs, versions, val = ent
-        if all(r() is t and t._version == v for r, v, t in zip(refs, versions, tensors)):
+        if all(r() is t and getattr(t, "_version", 0) == v for r, v, t in zip(refs, versions, tensors)):
             return val
         del _CACHE[key]
     val = make()
-    for k in [k for k, (refs, _, _) in _CACHE.items() if any(r() is None for r in refs)]:
+    try:
+        refs = [weakref.ref(t) for t in tensors]
+    except TypeError:  # a key object that cannot be weakly referenced: do not cache
+        return val
+    for k in [k for k, (rs, _, _) in _CACHE.items() if any(r() is None for r in rs)]:
         del _CACHE[k]  # entries whose source tensors are gone would only pin device memory
     if len(_CACHE) >= _CACHE_MAX:
         _CACHE.clear()
-    _CACHE[key] = ([weakref.ref(t) for t in tensors], [t._version for t in tensors], val)
+    _CACHE[key] = (refs, [getattr(t, "_version", 0) for t in tensors], val)
     return val
+
+
+def _normalizer_affine(norm, cout: int):
+    """``(scale, offset)`` lists of the output normaliser's affine map, computed on the host and cached per normaliser
+    object (+ the versions of its tensor parameters): the per-step call then neither copies nor synchronises, which also
+    keeps it legal inside CUDA-graph capture (GraphedMeasurementNorm)."""
+    params = getattr(norm, "params", None)
+    tensors = tuple(p for p in (params if isinstance(params, (tuple, list)) else ()) if isinstance(p, torch.Tensor))
+
+    def make():
+        ya, yb = _affine_of_normalizer(norm, True, cout, torch.device("cpu"), torch.float32)
+        return ya.tolist(), yb.tolist()
+
+    return _cached("yaffine", (norm,) + tensors, (cout,), make)
 
 
 def _kept_rows(mask1d: torch.Tensor) -> torch.Tensor:
@@ -213,8 +231,7 @@ def measurement_norm(model: SIRENAutodecoder_film, coords: torch.Tensor, latents
     if T * P == 0:
         raise ValueError("empty decode")
     if y_normalizer is not None:
-        ya, yb = _affine_of_normalizer(y_normalizer, True, cout, dev, torch.float32)
-        ya, yb = ya.tolist(), yb.tolist()
+        ya, yb = _normalizer_affine(y_normalizer, cout)
     else:
         ya, yb = [1.0] * cout, [0.0] * cout
     shape_key = (T, P, cout, tuple(out_lead), str(dev))

@@ -450,14 +450,17 @@ def test_graphed_measurement_norm_replays_with_new_latents(case, T, P, sensors):
     mask = torch.zeros(P, device="cuda")
     mask[torch.randperm(P, generator=torch.Generator().manual_seed(0))[:sensors].cuda()] = 1.0
     y_meas = (torch.randn(T, P, dims[2], generator=torch.Generator().manual_seed(3)) * 0.05).cuda()
-    graphed = cb.GraphedMeasurementNorm(m, c, lat.cuda()[:, None], y_meas, mask=mask)
+    # a normaliser whose parameters live on the HOST (the reference's normalizer_params.pt): nothing on the captured
+    # path may copy or synchronise because of it
+    yn = _Norm11([2.0, 1.5, 1.0, 0.5][:dims[2]], [-1.0, -1.5, -0.25, -0.5][:dims[2]])
+    graphed = cb.GraphedMeasurementNorm(m, c, lat.cuda()[:, None], y_meas, mask=mask, y_normalizer=yn)
     for seed in (11, 12, 13):
         new = (torch.randn(T, 1, dims[1], generator=torch.Generator().manual_seed(seed)) * 0.1).cuda()
         x_prev = new.clone().requires_grad_(True)
         n_g = graphed(1.5 * x_prev + 0.01)               # upstream op: the gradient must chain through it
         (g_g,) = torch.autograd.grad(n_g, x_prev)
         x2 = new.clone().requires_grad_(True)
-        n_e = cb.measurement_norm(m, c, 1.5 * x2 + 0.01, y_meas, mask=mask)
+        n_e = cb.measurement_norm(m, c, 1.5 * x2 + 0.01, y_meas, mask=mask, y_normalizer=yn)
         (g_e,) = torch.autograd.grad(n_e, x2)
         assert abs(float(n_g) - float(n_e)) <= 1e-6 * float(n_e)
         assert O.rel_l2(g_g, g_e) <= 1e-5
