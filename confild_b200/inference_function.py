@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import weakref
+
 import torch
 
 #: upper bound of decoded output bytes per kernel launch (frames per chunk follow from it); small enough that the
@@ -45,6 +47,39 @@ def _chunk_plan(t_size: int, m_size: int, cout: int, batch_size: int) -> list:
         rem -= take
         n = min(step, n * 3)
     return rev[::-1]
+
+
+# decoder(): the reference's affine normalisers ('-11', '01', 'ms', 'none') folded into layer 0 and the head of a cached copy of
+# the module, so that the field leaves the kernel in physical units -- the eager `denormalize` is 3-4 element-wise passes
+# over the whole decoded field (~1.3 ms per 805 MB on a B200).  One entry per module, validated by the identity of the
+# normaliser objects and by the module's parameter versions / w0 (the key the weight packing uses).
+_FOLDED: dict = {}
+
+
+def _folded_module(model, x_normalizer, y_normalizer):
+    """A module equal to ``y_normalizer.denormalize(model(x_normalizer.normalize(.), .))``, or None when the normalisers
+    are not the reference's affine kinds (the caller then applies them eagerly)."""
+    from .folding import fold_normalizers  # (local: folding imports nothing from here)
+
+    if not hasattr(model, "_ensure_packed") or not hasattr(model, "nl"):
+        return None
+    try:
+        params = list(model.parameters())
+        state = (tuple((p.data_ptr(), p._version) for p in params), float(model.nl.w0), str(params[0].device),
+                 getattr(model, "precision", None))
+        ent = _FOLDED.get(id(model))
+        if ent is not None:
+            mref, xref, yref, st, folded = ent
+            if mref() is model and xref() is x_normalizer and yref() is y_normalizer and st == state:
+                return folded
+        folded = fold_normalizers(model, x_normalizer, y_normalizer)
+        folded.eval()
+        if len(_FOLDED) >= 8:
+            _FOLDED.clear()
+        _FOLDED[id(model)] = (weakref.ref(model), weakref.ref(x_normalizer), weakref.ref(y_normalizer), state, folded)
+        return folded
+    except (ValueError, AttributeError, TypeError, RuntimeError):
+        return None
 
 
 def _out_features(model) -> int:
@@ -83,7 +118,13 @@ def decoder(coords, latents, model, x_normalizer, y_normalizer, batch_size, devi
     if out is None:
         out = torch.empty((t_size, m_size, cout), dtype=torch.float32, pin_memory=(dev.type == "cuda"))
     with torch.no_grad():
-        coords_n = x_normalizer.normalize(coords.reshape(1, m_size, coords_size).to(dev))
+        folded = _folded_module(model, x_normalizer, y_normalizer) if dev.type == "cuda" else None
+        if folded is not None:  # physical coordinates in, physical fields out: no element-wise pass around the kernel
+            model, coords_n = folded, coords.reshape(1, m_size, coords_size).to(dev)
+            denorm = lambda y: y  # noqa: E731
+        else:
+            coords_n = x_normalizer.normalize(coords.reshape(1, m_size, coords_size).to(dev))
+            denorm = y_normalizer.denormalize
         if dev.type != "cuda":
             for sid in range(0, t_size, step):
                 lat = latents[sid:sid + step].reshape(-1, 1, latent_size)
@@ -104,7 +145,7 @@ def decoder(coords, latents, model, x_normalizer, y_normalizer, batch_size, devi
             if i >= 3:
                 copied[i - 3].synchronize()
             lat = lat_dev[sid:sid + n]
-            chunk = y_normalizer.denormalize(model(coords_n, lat))
+            chunk = denorm(model(coords_n, lat))
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(copy_stream):

@@ -359,6 +359,56 @@ def test_reference_callers_shapes():
     assert host.device.type == "cpu" and O.rel_l2(host, want) < 1e-4
 
 
+def test_decoder_folds_affine_normalizers_and_falls_back_otherwise():
+    """decoder() folds the reference's affine normalisers into a cached copy of the module (no element-wise pass over the
+    decoded field); arbitrary normaliser objects are applied eagerly as before; the cached copy follows weight changes."""
+    from confild_b200 import inference_function as inf
+
+    dims = O.CASE_SHAPES["case1"]
+    sd = O.init_params(*dims, seed=0)
+    m = make_model(dims, sd, "f16f8")
+    T, P = 5, 700
+    coords, lat = O.synthetic_inputs(dims[0], dims[1], T, P)
+    phys = coords * 0.8 + 0.3
+
+    class N11(_Norm11):
+        def normalize(self, x):
+            hi, lo = (p.to(x.device) for p in self.params)
+            return (x - lo) / (hi - lo) * 2 - 1
+
+    xn = N11([1.5, 1.2], [-0.5, -0.7])
+    yn = N11([2.0, 1.5, 1.0], [-1.0, -1.5, -0.25])
+    want = yn.denormalize(O.forward(sd, xn.normalize(phys)[None], lat[:, None]))
+    inf._FOLDED.clear()
+    got = cb.decoder(phys, lat, m, xn, yn, 2, "cuda")
+    assert id(m) in inf._FOLDED and O.rel_l2(got, want) <= FWD_TOL["f16f8"]
+    folded_first = inf._FOLDED[id(m)][-1]
+    got2 = cb.decoder(phys, lat, m, xn, yn, 64, "cuda")
+    assert inf._FOLDED[id(m)][-1] is folded_first and torch.equal(got, got2)  # cache hit, chunking does not matter
+    with torch.no_grad():  # new weights: the folded copy must be rebuilt
+        for prm in m.parameters():
+            prm.mul_(0.9)
+    sd2 = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    want2 = yn.denormalize(O.forward(sd2, xn.normalize(phys)[None], lat[:, None]))
+    got3 = cb.decoder(phys, lat, m, xn, yn, 64, "cuda")
+    assert inf._FOLDED[id(m)][-1] is not folded_first and O.rel_l2(got3, want2) <= FWD_TOL["f16f8"]
+
+    class Odd:  # not one of the reference's methods: applied eagerly
+        method = "cubic"
+        params = None
+
+        def normalize(self, x):
+            return x * 0.5
+
+        def denormalize(self, y):
+            return y ** 3 + 1.0
+
+    odd = Odd()
+    want4 = odd.denormalize(O.forward(sd2, odd.normalize(phys)[None], lat[:, None]))
+    got4 = cb.decoder(phys, lat, m, odd, odd, 64, "cuda")
+    assert O.rel_l2(got4, want4) <= 3 * FWD_TOL["f16f8"]
+
+
 def test_folded_normalizers_on_gpu():
     """f2: normalise / denormalise / latent un-normalise folded into the weights -- no extra element-wise pass."""
     dims = O.CASE_SHAPES["case1"]
