@@ -66,14 +66,14 @@ def _folded_module(model, x_normalizer, y_normalizer):
     try:
         params = list(model.parameters())
         state = (tuple((p.data_ptr(), p._version) for p in params), float(model.nl.w0), str(params[0].device),
-                 getattr(model, "precision", None))
+                 getattr(model, "precision", None), bool(model.training), tuple(p.requires_grad for p in params))
         ent = _FOLDED.get(id(model))
         if ent is not None:
             mref, xref, yref, st, folded = ent
             if mref() is model and xref() is x_normalizer and yref() is y_normalizer and st == state:
                 return folded
-        folded = fold_normalizers(model, x_normalizer, y_normalizer)
-        folded.eval()
+        folded = fold_normalizers(model, x_normalizer, y_normalizer)  # (a deep copy: same mode and requires_grad flags,
+        # so the grad-mode checks of the module behave exactly as they would on the original)
         if len(_FOLDED) >= 8:
             _FOLDED.clear()
         _FOLDED[id(model)] = (weakref.ref(model), weakref.ref(x_normalizer), weakref.ref(y_normalizer), state, folded)
@@ -94,12 +94,16 @@ def pass_through_model_batch(coords, latents, model, x_normalizer, y_normalizer,
     """
     t_size, latent_size = latents.shape
     m_size, coords_size = coords.shape
-    coords_n = x_normalizer.normalize(coords.reshape(1, m_size, coords_size).to(device))
     step = _frames_per_chunk(t_size, m_size, _out_features(model), batch_size)
+    folded = _folded_module(model, x_normalizer, y_normalizer) if torch.device(device).type == "cuda" else None
+    if folded is not None:  # affine normalisers folded into the weights: no element-wise pass (nor its autograd mirror)
+        model, coords_n, denorm = folded, coords.reshape(1, m_size, coords_size).to(device), (lambda y: y)
+    else:
+        coords_n, denorm = x_normalizer.normalize(coords.reshape(1, m_size, coords_size).to(device)), y_normalizer.denormalize
     outs = []
     for sid in range(0, t_size, step):
         batch_latent = latents[sid:sid + step].reshape(-1, 1, latent_size)
-        outs.append(y_normalizer.denormalize(model(coords_n, batch_latent)))
+        outs.append(denorm(model(coords_n, batch_latent)))
     return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
 
